@@ -1,0 +1,635 @@
+// Host drivers of the four samplers: chain state in HBM, per-iteration launch sequence
+//   [host shuffle -> H2D]  gram kernel  ->  persistent sweep kernel  ->  hyper-parameter kernel(s)  [-> row snapshot D2H]
+// and the C ABI on top of it.  Mirrors the driver loops of the reference (src/BayesRv2.cpp:146-274,
+// src/BayesRv2Groups.cpp:170-333, src/BRv2Grstart.cpp:155-282, src/HorseshoeR.cpp:168-264); nothing here computes on
+// the CPU except initial scalars, the O(M) marker shuffle (std::random_shuffle in the reference, :182) and row packing.
+#include "sweep.cuh"
+#include "hyper.cuh"
+#include "writer.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+using namespace brr;
+
+namespace {
+
+constexpr int PERM_RING = 3, ROW_RING = 2;
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    void alloc(size_t count) { release(); n = count; if (count) BRR_CUDA(cudaMalloc(&p, count * sizeof(T))); }
+    void zero(cudaStream_t s = 0) { if (p) BRR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const T *h, size_t count) { if (count) BRR_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
+    void from(const std::vector<T> &v) { alloc(v.size()); upload(v.data(), v.size()); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+template <class T> struct PinBuf {
+    T *p = nullptr; size_t n = 0;
+    void alloc(size_t count) { release(); n = count; if (count) BRR_CUDA(cudaMallocHost(&p, count * sizeof(T))); }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+    ~PinBuf() { release(); }
+};
+
+struct RowSnap {            // one in-flight sample row
+    PinBuf<double> row;     // full row, reference layout
+    PinBuf<double> scal;    // IterScalars (as bytes) followed by sigmaG[G]
+    cudaEvent_t ready = nullptr;
+    bool pending = false;
+    int64_t it = -1;
+};
+
+}  // namespace
+
+struct brr_chain {
+    brr_geno *g = nullptr;
+    int kind = 0, K = 0, G = 1; int64_t N = 0, M = 0, F = 0;
+    uint64_t seed = 0; PhiloxKey key{0, 0};
+    int max_iterations = 0, burn_in = 0, thinning = 1;
+    double sigma0 = 0, v0E = 0, s02E = 0, v0G = 0, s02G = 0;
+    double A = 0, vL = 0, vT = 0, c2 = 0, vC = 0, sC = 0;
+    std::vector<double> Y, cva, pi_init, fixed, beta0, sigmaGG0, eps0, comp0;
+    std::vector<int32_t> gAssign;
+    double mu0 = 0, sigmaE0 = 0;
+    int gram_impl = 0;
+    // geometry
+    int B = 128, TW = 1, nW = 1, seg_bytes = 16, PS = 128, nb = 0; size_t smem = 0;
+    // device state
+    DevBuf<double> eps, beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
+    DevBuf<double> partials, bcast, fin;
+    DevBuf<int32_t> d_gAssign, unit0, gram;
+    DevBuf<IterScalars> sc;
+    DevBuf<unsigned> sync;
+    DevBuf<int> abort_flag;
+    PinBuf<int32_t> h_perm[PERM_RING]; DevBuf<int32_t> d_perm[PERM_RING]; cudaEvent_t perm_free[PERM_RING] = {}; bool perm_used[PERM_RING] = {};
+    std::vector<int32_t> markerI, fixedI;
+    // replay
+    bool replay = false; int64_t rp_iters = 0, rp_ngam = 0;
+    DevBuf<double> rp_u, rp_z, rp_mu, rp_gam, rp_fixz, rp_nu, rp_lam;
+    std::vector<int32_t> rp_perm, rp_fixperm; std::vector<double> rp_init_u, rp_init_g, rp_mu_h, rp_gam_h, rp_nu_h;
+    // rows
+    RowSnap snaps[ROW_RING]; int64_t snap_seq = 0, deliver_seq = 0;
+    std::unique_ptr<SampleWriter> writer;
+    int64_t it = 0; bool initialised = false;
+    cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0; int64_t last_launches = 0;
+
+    int64_t row_len() const
+    {
+        switch (kind) {
+        case BRR_V2: return 2 * M + 4 + N;                   // reference src/BayesRv2.cpp:136
+        case BRR_GROUPS: return 2 * M + 3 + G + N + F + 1;   // src/BayesRv2Groups.cpp:152
+        case BRR_GRSTART: return 2 * M + 3 + G + N;          // src/BRv2Grstart.cpp:140
+        default: return 2 * M + 4 + N;                       // src/HorseshoeR.cpp:157
+        }
+    }
+    ~brr_chain()
+    {
+        if (g) cudaSetDevice(g->device);
+        for (auto &e : perm_free) if (e) cudaEventDestroy(e);
+        for (auto &s : snaps) if (s.ready) cudaEventDestroy(s.ready);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+double host_sum(const double *x, int64_t n) { long double s = 0; for (int64_t i = 0; i < n; ++i) s += x[i]; return (double)s; }
+double host_sqnorm(const double *x, int64_t n) { long double s = 0; for (int64_t i = 0; i < n; ++i) s += (long double)x[i] * x[i]; return (double)s; }
+
+double init_uniform(brr_chain *c, int64_t idx)
+{
+    if (c->replay) { BRR_REQUIRE(idx < (int64_t)c->rp_init_u.size(), BRR_E_ARG, "replay: init_u too short"); return c->rp_init_u[idx]; }
+    return draw_uniform(c->key, S_INIT_U, -1, idx);
+}
+double init_gamma(brr_chain *c, int64_t idx, double shape)
+{
+    if (c->replay) { BRR_REQUIRE(idx < (int64_t)c->rp_init_g.size(), BRR_E_ARG, "replay: init_g too short"); return c->rp_init_g[idx]; }
+    return draw_gamma(c->key, S_INIT_G, -1, idx, shape);
+}
+
+void choose_geometry(brr_chain *c, int want_block, int want_workers)
+{
+    int dev = 0, sms = 0;
+    BRR_CUDA(cudaGetDevice(&dev));
+    BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int kidx = c->kind == BRR_HORSESHOE ? 1 : 0;
+    BRR_REQUIRE(c->kind == BRR_HORSESHOE || (c->K >= 2 && c->K <= KMAX), BRR_E_SIZE,
+                "number of mixture components must be in [2, " + std::to_string(KMAX) + "]");
+    const int64_t units = (c->N + 63) / 64;
+    int B = want_block ? want_block : 128;
+    BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
+    int nW = want_workers > 0 ? want_workers : sms - 1;
+    nW = (int)std::max<int64_t>(1, std::min<int64_t>(nW, units));
+    while (true) {
+        const int64_t maxu = (units + nW - 1) / nW;
+        const int words = (int)maxu * 4;
+        const int TW = words <= 32 ? 1 : words <= 64 ? 2 : words <= 128 ? 4 : 0;
+        BRR_REQUIRE(TW != 0, BRR_E_SIZE, "more than 2048 rows per worker CTA (" + std::to_string(maxu * 64) +
+                    "): shard the individuals over more devices");
+        const int seg = (int)maxu * 16;
+        const size_t smem = sweep_smem_bytes(kidx, B, c->K, c->G, (int)c->F, seg);
+        if (smem > 227 * 1024) {
+            BRR_REQUIRE(B > 32, BRR_E_SIZE, "sweep kernel does not fit shared memory (reduce K or groups)");
+            B /= 2; continue;
+        }
+        const int cores = sweep_max_coresident(kidx, B, TW, smem);
+        BRR_REQUIRE(cores >= 2, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
+        if (nW + 1 > cores) { nW = cores - 1; continue; }
+        c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->smem = smem;
+        break;
+    }
+    c->PS = (int)std::max<int64_t>(c->B, c->F);
+    c->nb = (int)((c->M + c->B - 1) / c->B);
+    std::vector<int32_t> u0(c->nW + 1);
+    for (int w = 0; w <= c->nW; ++w) u0[w] = (int32_t)(units * w / c->nW);
+    c->unit0.from(u0);
+}
+
+// ---- lazy initialisation: everything the reference does before `for (iteration ...)`
+void chain_init(brr_chain *c)
+{
+    const int64_t N = c->N, M = c->M, F = c->F; const int K = c->K, G = c->G;
+    BRR_CUDA(cudaSetDevice(c->g->device));
+    IterScalars sc; memset(&sc, 0, sizeof sc);
+    std::vector<double> eps(c->g->Npad, 0.0), beta(M, 0.0), comp(M, 0.0), sigG(G, 0.0), pi((size_t)G * std::max(K, 1), 0.0);
+    double mu = 0.0;
+    if (c->kind == BRR_V2) {
+        sigG[0] = init_uniform(c, 0);                                                   // src/BayesRv2.cpp:162
+        for (int k = 0; k < K; ++k) pi[k] = c->pi_init[k];                              // :150,:164 (Q1)
+        for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu - 0.0;                    // :168 (beta == 0)
+        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :169
+    } else if (c->kind == BRR_GROUPS) {
+        for (int g = 0; g < G; ++g) { pi[(size_t)g * K] = 0.5; for (int k = 1; k < K; ++k) pi[(size_t)g * K + k] = 0.5 / K; }   // Groups:170-175
+        for (int g = 0; g < G; ++g) sigG[g] = init_uniform(c, g);                       // :194-195
+        sc.sigmaF = init_uniform(c, G);                                                 // :197
+        for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu;                          // :203
+        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :204
+    } else if (c->kind == BRR_GRSTART) {
+        mu = c->mu0; sc.sigmaE = c->sigmaE0;
+        beta = c->beta0; comp = c->comp0; sigG = c->sigmaGG0;
+        std::copy(c->eps0.begin(), c->eps0.end(), eps.begin());
+        std::vector<double> v((size_t)G * K, 0.0);
+        for (int64_t i = 0; i < M; ++i) {                                               // Grstart:159-162
+            const int k = (int)comp[i], g = c->gAssign[i];
+            BRR_REQUIRE(k >= 0 && k < K, BRR_E_ARG, "components entry outside [0, K)");
+            v[(size_t)g * K + k] += 1.0;
+        }
+        for (int g = 0; g < G; ++g) {                                                   // :163-165
+            double s = 0; std::vector<double> gg(K);
+            for (int k = 0; k < K; ++k) gg[k] = 1.0 * init_gamma(c, (int64_t)g * (K + 1) + 1 + k, v[(size_t)g * K + k] + 1.0);
+            { double s0 = 0, s1 = 0, s2 = 0, s3 = 0; int i = 0;
+              for (; i + 4 <= K; i += 4) { s0 += gg[i]; s1 += gg[i + 1]; s2 += gg[i + 2]; s3 += gg[i + 3]; }
+              s = (s0 + s2) + (s1 + s3); for (; i < K; ++i) s += gg[i]; }
+            for (int k = 0; k < K; ++k) pi[(size_t)g * K + k] = gg[k] / s;
+        }
+    } else {
+        for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu - 0.0;                    // HorseshoeR.cpp:186
+        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :187
+        // :171,:176,:179 draw and discard (tau, v, lambda are overwritten at :177,:180,:192); keyed draws need not be consumed
+        const double eta0 = 1.0 / ((1.0 / (1 / (sc.sigmaE * std::pow(c->A, 2)))) * init_gamma(c, 2 * M, 0.5));       // :189
+        sc.eta = eta0;
+        sc.tau = (1.0 / eta0) * (1.0 / ((1.0 / c->vT) * init_gamma(c, 2 * M + 1, 0.5 * c->vT)));                      // :192
+        sc.c2 = c->c2;
+        std::vector<double> lam(M, 1.0), nu(M);
+        // eta and nu of iteration 0 (:217-218) -- the per-iteration kernels draw them for iteration it+1 afterwards
+        const double ge = c->replay ? c->rp_gam_h[0] : draw_gamma(c->key, S_GAMMA, 0, 0, 0.5 + 0.5 * c->vT);
+        sc.eta_next = 1.0 / ((1.0 / ((1.0 / (sc.sigmaE * c->A * c->A)) + c->vT / sc.tau)) * ge);
+        for (int64_t j = 0; j < M; ++j) {
+            const double gn = c->replay ? c->rp_nu_h[j] : draw_gamma(c->key, S_HS_NU, 0, j, 0.5 + 0.5 * c->vL);
+            nu[j] = 1.0 / ((1.0 / (c->vL / lam[j] + 1.0)) * gn);
+        }
+        c->lambda.from(lam); c->nu.from(nu);
+        c->hs_part.alloc((size_t)((M + 255) / 256) * 2);
+    }
+    // first intercept draw (:177-179 of iteration 0)
+    {
+        const double es = host_sum(eps.data(), N), n = (double)N;
+        const double z = c->replay ? c->rp_mu_h[0] : draw_normal(c->key, S_MU, 0, 0);
+        sc.mu = mu;
+        sc.mu_next = (es + n * mu) / n + std::sqrt(sc.sigmaE / n) * z;
+        sc.shift = mu - sc.mu_next;
+        sc.eps_sum = es + n * sc.shift;
+    }
+    c->eps.from(eps); c->beta.from(beta); c->comp.from(comp); c->sigmaG.from(sigG); c->pi.from(pi);
+    c->vcount.alloc((size_t)G * std::max(K, 1)); c->vcount.zero(); c->betaAcum.alloc(G); c->betaAcum.zero();
+    if (c->kind != BRR_HORSESHOE) c->d_cva.from(c->cva);
+    if (!c->gAssign.empty()) c->d_gAssign.from(c->gAssign);
+    if (F > 0) {
+        c->d_fixed.from(c->fixed);
+        std::vector<double> fg((size_t)F * F + F, 0.0), al(F, 0.0);
+        for (int64_t a = 0; a < F; ++a) {
+            for (int64_t b = 0; b < F; ++b) {
+                long double s = 0; const double *fa = &c->fixed[a * N], *fb = &c->fixed[b * N];
+                for (int64_t i = 0; i < N; ++i) s += (long double)fa[i] * fb[i];
+                fg[a * F + b] = (double)s;
+            }
+            fg[(size_t)F * F + a] = host_sum(&c->fixed[a * N], N);
+        }
+        c->fixG.from(fg); c->alpha.from(al);
+    }
+    std::vector<IterScalars> scv(1, sc); c->sc.from(scv);
+    c->partials.alloc((size_t)c->nW * c->PS); c->partials.zero();
+    c->bcast.alloc((size_t)3 * c->PS); c->bcast.zero();
+    c->fin.alloc((size_t)2 * c->nW); c->fin.zero();
+    c->sync.alloc(2);
+    c->abort_flag.alloc(1); c->abort_flag.zero();
+    c->gram.alloc((size_t)c->nb * c->B * c->B);
+    const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
+    for (int i = 0; i < PERM_RING; ++i) {
+        c->h_perm[i].alloc(pn); c->d_perm[i].alloc(pn);
+        BRR_CUDA(cudaEventCreateWithFlags(&c->perm_free[i], cudaEventDisableTiming));
+    }
+    c->markerI.resize(M); for (int64_t i = 0; i < M; ++i) c->markerI[i] = (int32_t)i;   // :137-140
+    c->fixedI.resize(F); for (int64_t i = 0; i < F; ++i) c->fixedI[i] = (int32_t)i;
+    for (auto &s : c->snaps) {
+        s.row.alloc((size_t)c->row_len()); s.scal.alloc(sizeof(IterScalars) / 8 + 1 + (size_t)G);
+        BRR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+    }
+    BRR_CUDA(cudaDeviceSynchronize());
+    c->initialised = true;
+}
+
+void deliver_row(brr_chain *c, RowSnap &s, double *rows, int64_t max_rows, int64_t *n_rows)
+{
+    BRR_CUDA(cudaEventSynchronize(s.ready));
+    const int64_t N = c->N, M = c->M, F = c->F; const int G = c->G;
+    IterScalars sc; memcpy(&sc, s.scal.p, sizeof sc);
+    const double *sg = s.scal.p + sizeof(IterScalars) / 8 + 1;
+    double *r = s.row.p;
+    r[0] = (double)s.it; r[1] = sc.mu;
+    switch (c->kind) {
+    case BRR_V2: r[2 + M] = sc.sigmaE; r[3 + M] = sg[0]; break;                         // src/BayesRv2.cpp:260
+    case BRR_GROUPS:                                                                     // src/BayesRv2Groups.cpp:317
+        r[2 + M] = sc.sigmaE; for (int g = 0; g < G; ++g) r[3 + 2 * M + g] = sg[g];
+        r[3 + 2 * M + G + N + F] = sc.sigmaF; break;
+    case BRR_GRSTART: r[2 + M] = sc.sigmaE; for (int g = 0; g < G; ++g) r[3 + 2 * M + g] = sg[g]; break;   // src/BRv2Grstart.cpp:267
+    default: r[2 + M] = sc.sigmaE; r[3 + M] = sc.tau; break;                             // src/HorseshoeR.cpp:258
+    }
+    const int64_t L = c->row_len();
+    if (rows && *n_rows < max_rows) memcpy(rows + *n_rows * L, r, (size_t)L * 8);
+    if (c->writer) c->writer->enqueue(r, (size_t)L);                                     // q.enqueue(sample)  :261
+    ++*n_rows;
+    s.pending = false;
+}
+
+void snapshot_row(brr_chain *c, int64_t it, double *rows, int64_t max_rows, int64_t *n_rows)
+{
+    RowSnap &s = c->snaps[c->snap_seq % ROW_RING];
+    if (s.pending) { deliver_row(c, s, rows, max_rows, n_rows); ++c->deliver_seq; }
+    const int64_t N = c->N, M = c->M, F = c->F; const int G = c->G;
+    double *r = s.row.p; cudaStream_t st = c->stream;
+    auto d2h = [&](double *dst, const double *src, int64_t n) { if (n) BRR_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, st)); };
+    d2h(r + 2, c->beta.p, M);
+    switch (c->kind) {
+    case BRR_V2: d2h(r + 4 + M, c->comp.p, M); d2h(r + 4 + 2 * M, c->eps.p, N); break;
+    case BRR_GROUPS: d2h(r + 3 + M, c->comp.p, M); d2h(r + 3 + 2 * M + G, c->eps.p, N); d2h(r + 3 + 2 * M + G + N, c->alpha.p, F); break;
+    case BRR_GRSTART: d2h(r + 3 + M, c->comp.p, M); d2h(r + 3 + 2 * M + G, c->eps.p, N); break;
+    default: d2h(r + 4 + M, c->lambda.p, M); d2h(r + 4 + 2 * M, c->eps.p, N); break;
+    }
+    BRR_CUDA(cudaMemcpyAsync(s.scal.p, c->sc.p, sizeof(IterScalars), cudaMemcpyDeviceToHost, st));
+    d2h(s.scal.p + sizeof(IterScalars) / 8 + 1, c->sigmaG.p, G);
+    BRR_CUDA(cudaEventRecord(s.ready, st));
+    s.pending = true; s.it = it;
+    ++c->snap_seq;
+}
+
+void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows)
+{
+    BRR_CUDA(cudaSetDevice(c->g->device));
+    if (!c->initialised) chain_init(c);
+    const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
+    const int kk = c->kind == BRR_HORSESHOE ? 1 : 0;
+    int64_t launches = 0;
+    BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int n = 0; n < n_iter; ++n) {
+        const int64_t it = c->it;
+        const bool rp = c->replay;
+        if (rp) BRR_REQUIRE(it < c->rp_iters, BRR_E_ARG, "replay tables exhausted");
+        const int slot = (int)(it % PERM_RING);
+        if (c->perm_used[slot]) BRR_CUDA(cudaEventSynchronize(c->perm_free[slot]));
+        int32_t *hp = c->h_perm[slot].p;
+        if (rp) memcpy(hp, &c->rp_perm[(size_t)it * M], (size_t)M * 4);
+        else { shuffle_host(c->key, S_PERM, it, c->markerI.data(), M); memcpy(hp, c->markerI.data(), (size_t)M * 4); }   // :182
+        const size_t fo = (size_t)c->nb * c->B;
+        if (F > 0) {
+            if (rp) memcpy(hp + fo, &c->rp_fixperm[(size_t)it * F], (size_t)F * 4);
+            else { shuffle_host(c->key, S_FIXPERM, it, c->fixedI.data(), F); memcpy(hp + fo, c->fixedI.data(), (size_t)F * 4); }   // Groups:216
+        }
+        BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p, hp, (size_t)(M) * 4, cudaMemcpyHostToDevice, c->stream));
+        if (F > 0) BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p + fo, hp + fo, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream));
+        c->perm_used[slot] = true;
+
+        launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
+        BRR_CUDA(cudaMemsetAsync(c->sync.p, 0, 2 * sizeof(unsigned), c->stream));
+
+        SweepParams p; memset(&p, 0, sizeof p);
+        const brr_geno *g = c->g;
+        p.packed = g->d_packed; p.stride = g->stride; p.N = g->N;
+        p.colA = g->d_a; p.colD = g->d_d; p.colS = g->d_S; p.colXsq = g->d_xsq; p.colCsum = g->d_csum; p.n_total = g->n_total;
+        p.perm = c->d_perm[slot].p; p.gram = c->gram.p; p.M = M; p.nb = c->nb; p.it = it;
+        p.eps = c->eps.p; p.beta = c->beta.p; p.comp = c->comp.p; p.sc = c->sc.p;
+        p.K = K; p.G = G; p.gAssign = c->d_gAssign.p; p.cva = c->d_cva.p; p.sigmaG = c->sigmaG.p; p.pi = c->pi.p;
+        p.vcount = c->vcount.p; p.betaAcum = c->betaAcum.p; p.lambda = c->lambda.p;
+        p.key = c->key;
+        p.tbl_u = rp && c->rp_u.p ? c->rp_u.p + (size_t)it * M : nullptr;
+        p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
+        p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
+        p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
+        p.arrive = c->sync.p; p.go = c->sync.p + 1; p.abort_flag = c->abort_flag.p; p.partials = c->partials.p; p.bcast = c->bcast.p; p.fin = c->fin.p;
+        p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
+        launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
+        BRR_CUDA(cudaEventRecord(c->perm_free[slot], c->stream));
+
+        HyperParams h; memset(&h, 0, sizeof h);
+        h.kind = c->kind; h.it = it; h.n_total = g->n_total; h.M = M; h.K = K; h.G = G; h.F = F;
+        h.v0E = c->v0E; h.s02E = c->s02E; h.v0G = c->v0G; h.s02G = c->s02G;
+        h.sc = c->sc.p; h.sigmaG = c->sigmaG.p; h.pi = c->pi.p; h.vcount = c->vcount.p; h.betaAcum = c->betaAcum.p;
+        h.beta = c->beta.p; h.alpha = c->alpha.p; h.fin = c->fin.p; h.nW = c->nW; h.key = c->key;
+        const bool next_in = rp && it + 1 < c->rp_iters;
+        h.tbl_gam = rp && c->rp_gam.p ? c->rp_gam.p + (size_t)it * c->rp_ngam : nullptr;
+        h.tbl_gam_next = next_in && c->rp_gam.p ? c->rp_gam.p + (size_t)(it + 1) * c->rp_ngam : nullptr;
+        h.tbl_mu_z_next = next_in && c->rp_mu.p ? c->rp_mu.p + (it + 1) : nullptr;
+        h.A = c->A; h.vL = c->vL; h.vT = c->vT; h.vC = c->vC; h.sC = c->sC;
+        h.lambda = c->lambda.p; h.nu = c->nu.p; h.hs_part = c->hs_part.p;
+        h.tbl_hs_lam = rp && c->rp_lam.p ? c->rp_lam.p + (size_t)it * M : nullptr;
+        h.tbl_hs_nu_next = next_in && c->rp_nu.p ? c->rp_nu.p + (size_t)(it + 1) * M : nullptr;
+        launch_hyper(h, c->stream);
+        launches += 2 + hyper_launch_count(c->kind);
+
+        if (emit_all || (it >= c->burn_in && it % c->thinning == 0))                     // :257-259
+            snapshot_row(c, it, rows, max_rows, n_rows);
+        ++c->it;
+    }
+    BRR_CUDA(cudaEventRecord(c->ev1, c->stream));
+    BRR_CUDA(cudaStreamSynchronize(c->stream));
+    {
+        int flag = 0;
+        BRR_CUDA(cudaMemcpy(&flag, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+        BRR_REQUIRE(flag == 0, BRR_E_CUDA, "sweep kernel watchdog fired (code " + std::to_string(flag) + "): grid hand-over timed out");
+    }
+    while (c->deliver_seq < c->snap_seq) {
+        RowSnap &s = c->snaps[c->deliver_seq % ROW_RING];
+        if (s.pending) deliver_row(c, s, rows, max_rows, n_rows);
+        ++c->deliver_seq;
+    }
+    float ms = 0; BRR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms; c->last_launches = launches;
+}
+
+void check_iters(int max_iterations, int burn_in, int thinning)
+{
+    // the only validation of the reference that returns (src/BayesRv2.cpp:76-80)
+    BRR_REQUIRE(!(max_iterations < burn_in || max_iterations < 1 || burn_in < 1), BRR_E_ITER,
+                "error: burn_in has to be a positive integer and smaller than the maximum number of iterations");
+    BRR_REQUIRE(thinning >= 1, BRR_E_ARG, "thinning must be >= 1 (the reference divides by it, src/BayesRv2.cpp:259)");
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **out)
+{
+    return guarded([&] {
+        BRR_REQUIRE(cfg && g && out, BRR_E_ARG, "brr_chain_create: null pointer");
+        BRR_REQUIRE(cfg->kind >= BRR_V2 && cfg->kind <= BRR_HORSESHOE, BRR_E_ARG, "unknown sampler kind");
+        check_iters(cfg->max_iterations, cfg->burn_in, cfg->thinning);
+        require_device(g->device);
+        std::unique_ptr<brr_chain> c(new brr_chain());
+        c->g = g; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
+        c->seed = cfg->seed; c->key = PhiloxKey{ (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32) };
+        c->max_iterations = cfg->max_iterations; c->burn_in = cfg->burn_in; c->thinning = cfg->thinning;
+        c->sigma0 = cfg->sigma0; c->v0E = cfg->v0E; c->s02E = cfg->s02E; c->v0G = cfg->v0G; c->s02G = cfg->s02G;
+        c->gram_impl = cfg->gram_impl;
+        const int64_t N = c->N, M = c->M;
+        if (cfg->kind != BRR_GRSTART) { BRR_REQUIRE(cfg->Y, BRR_E_ARG, "Y is null"); c->Y.assign(cfg->Y, cfg->Y + N); }
+        if (cfg->kind == BRR_HORSESHOE) {
+            c->K = 0; c->G = 1;
+            c->A = cfg->A; c->vL = cfg->vL; c->vT = cfg->vT; c->c2 = cfg->c2; c->vC = cfg->vC; c->sC = cfg->sC;
+        } else {
+            BRR_REQUIRE(cfg->cva && cfg->ncva >= 1, BRR_E_ARG, "cva is null or empty");
+            c->K = cfg->ncva + 1;
+            c->G = cfg->kind == BRR_V2 ? 1 : cfg->groups;
+            BRR_REQUIRE(c->G >= 1, BRR_E_ARG, "groups must be >= 1");
+            BRR_REQUIRE((int64_t)c->G * (c->K + 1) <= 4096, BRR_E_SIZE, "groups x components too large for the in-kernel tables");
+            c->cva.assign(cfg->cva, cfg->cva + (size_t)c->G * cfg->ncva);
+            if (cfg->kind != BRR_V2) {
+                BRR_REQUIRE(cfg->gAssign, BRR_E_ARG, "gAssign is null");
+                c->gAssign.assign(cfg->gAssign, cfg->gAssign + M);
+                for (int64_t i = 0; i < M; ++i) BRR_REQUIRE(c->gAssign[i] >= 0 && c->gAssign[i] < c->G, BRR_E_ARG, "gAssign entry outside [0, groups)");
+            }
+            if (cfg->kind == BRR_V2) {
+                c->pi_init.resize(c->K);
+                if (cfg->pi_init) std::copy(cfg->pi_init, cfg->pi_init + c->K, c->pi_init.begin());
+                else {   // evident intent of src/BayesRv2.cpp:148-150
+                    double s = 0; for (int k = 0; k < cfg->ncva; ++k) s += cfg->cva[k];
+                    c->pi_init[0] = 0.5; for (int k = 1; k < c->K; ++k) c->pi_init[k] = 0.5 * cfg->cva[k - 1] / s;
+                }
+            }
+            if (cfg->kind == BRR_GROUPS && cfg->F > 0) {
+                BRR_REQUIRE(cfg->fixed, BRR_E_ARG, "fixed is null but F > 0");
+                c->F = cfg->F; c->fixed.assign(cfg->fixed, cfg->fixed + (size_t)N * cfg->F);
+            }
+            if (cfg->kind == BRR_GRSTART) {
+                BRR_REQUIRE(cfg->beta0 && cfg->sigmaGG0 && cfg->epsilon0 && cfg->components0, BRR_E_ARG, "restart state has a null pointer");
+                c->mu0 = cfg->mu0; c->sigmaE0 = cfg->sigmaE0;
+                c->beta0.assign(cfg->beta0, cfg->beta0 + M); c->sigmaGG0.assign(cfg->sigmaGG0, cfg->sigmaGG0 + c->G);
+                c->eps0.assign(cfg->epsilon0, cfg->epsilon0 + N); c->comp0.assign(cfg->components0, cfg->components0 + M);
+            }
+        }
+        choose_geometry(c.get(), cfg->block, cfg->workers);
+        BRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        BRR_CUDA(cudaEventCreate(&c->ev0)); BRR_CUDA(cudaEventCreate(&c->ev1));
+        *out = c.release();
+    });
+}
+
+extern "C" int brr_chain_set_replay(brr_chain *c, const brr_replay *r)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && r, BRR_E_ARG, "null pointer");
+        BRR_REQUIRE(!c->initialised, BRR_E_ARG, "replay tables must be set before the first brr_chain_run");
+        BRR_REQUIRE(r->M == c->M && r->n_iter >= 1 && r->perm && r->mu_z, BRR_E_ARG, "replay tables do not match the chain");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        const size_t T = (size_t)r->n_iter, M = (size_t)c->M, F = (size_t)c->F;
+        c->rp_iters = r->n_iter; c->rp_ngam = r->n_gam;
+        c->rp_perm.assign(r->perm, r->perm + T * M);
+        for (size_t i = 0; i < T * M; ++i) BRR_REQUIRE(c->rp_perm[i] >= 0 && c->rp_perm[i] < c->M, BRR_E_ARG, "replay perm entry out of range");
+        if (F) { BRR_REQUIRE(r->fixperm && r->fix_z && r->F == c->F, BRR_E_ARG, "replay: fixed-effect tables missing");
+                 c->rp_fixperm.assign(r->fixperm, r->fixperm + T * F); c->rp_fixz.alloc(T * F); c->rp_fixz.upload(r->fix_z, T * F); }
+        c->rp_mu_h.assign(r->mu_z, r->mu_z + T); c->rp_mu.alloc(T); c->rp_mu.upload(r->mu_z, T);
+        if (r->mark_u) { c->rp_u.alloc(T * M); c->rp_u.upload(r->mark_u, T * M); }
+        if (r->mark_z) { c->rp_z.alloc(T * M); c->rp_z.upload(r->mark_z, T * M); }
+        BRR_REQUIRE(r->gam && r->n_gam >= 1, BRR_E_ARG, "replay: gamma table missing");
+        c->rp_gam_h.assign(r->gam, r->gam + T * (size_t)r->n_gam);
+        c->rp_gam.alloc(T * (size_t)r->n_gam); c->rp_gam.upload(r->gam, T * (size_t)r->n_gam);
+        if (c->kind == BRR_HORSESHOE) {
+            BRR_REQUIRE(r->hs_nu && r->hs_lam, BRR_E_ARG, "replay: horseshoe tables missing");
+            c->rp_nu_h.assign(r->hs_nu, r->hs_nu + M);
+            c->rp_nu.alloc(T * M); c->rp_nu.upload(r->hs_nu, T * M);
+            c->rp_lam.alloc(T * M); c->rp_lam.upload(r->hs_lam, T * M);
+        } else BRR_REQUIRE(r->mark_u, BRR_E_ARG, "replay: mark_u missing");
+        if (r->init_u && r->n_init_u > 0) c->rp_init_u.assign(r->init_u, r->init_u + r->n_init_u);
+        if (r->init_g && r->n_init_g > 0) c->rp_init_g.assign(r->init_g, r->init_g + r->n_init_g);
+        c->replay = true;
+    });
+}
+
+extern "C" int brr_chain_open_output(brr_chain *c, const char *path)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && path, BRR_E_ARG, "null pointer");
+        c->writer.reset(new SampleWriter(path, sample_header(c->kind, c->N, c->M, c->G, c->F), c->kind != BRR_HORSESHOE));
+    });
+}
+extern "C" int brr_chain_close_output(brr_chain *c)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
+        if (c->writer) { std::unique_ptr<SampleWriter> w(std::move(c->writer)); w->finish(); }
+    });
+}
+extern "C" int64_t brr_chain_row_len(const brr_chain *c) { return c ? c->row_len() : -1; }
+
+extern "C" int brr_chain_run(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && n_iter >= 0, BRR_E_ARG, "bad arguments");
+        int64_t produced = 0;
+        run_iterations(c, n_iter, emit_all, rows, max_rows, &produced);
+        if (n_rows) *n_rows = produced;
+    });
+}
+extern "C" int brr_chain_get_pi(brr_chain *c, double *pi)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && pi && c->initialised && c->kind != BRR_HORSESHOE, BRR_E_ARG, "bad arguments");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        BRR_CUDA(cudaMemcpy(pi, c->pi.p, (size_t)c->G * c->K * 8, cudaMemcpyDeviceToHost));
+    });
+}
+extern "C" int brr_chain_get_hyper(brr_chain *c, double *out)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && out && c->initialised, BRR_E_ARG, "bad arguments");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        IterScalars sc; BRR_CUDA(cudaMemcpy(&sc, c->sc.p, sizeof sc, cudaMemcpyDeviceToHost));
+        out[0] = sc.eta; out[1] = sc.tau; out[2] = sc.c2;
+    });
+}
+extern "C" int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
+        if (ms) *ms = c->last_ms;
+        if (launches) *launches = c->last_launches;
+    });
+}
+extern "C" void brr_chain_destroy(brr_chain *c)
+{
+    if (!c) return;
+    try { if (c->writer) c->writer->finish(); } catch (...) { }
+    delete c;
+}
+
+// =================================================================================================
+// The four reference entry points
+namespace {
+
+struct GenoGuard { brr_geno *g = nullptr; ~GenoGuard() { brr_geno_free(g); } };
+struct ChainGuard { brr_chain *c = nullptr; ~ChainGuard() { brr_chain_destroy(c); } };
+
+void check_rc(int rc) { if (rc != BRR_OK) throw Error(rc, brr_last_error()); }
+
+void touch_file(const char *path, const std::string &header)
+{
+    FILE *f = fopen(path, "w");
+    BRR_REQUIRE(f, BRR_E_IO, std::string("cannot open output file '") + path + "'");
+    if (!header.empty()) fwrite(header.data(), 1, header.size(), f);
+    fclose(f);
+}
+
+void run_entry(const char *outputFile, const brr_config &cfg, const double *X, int64_t N, int64_t M)
+{
+    GenoGuard gg; ChainGuard cg;
+    check_rc(brr_geno_from_dense(X, N, M, 0, &gg.g));
+    check_rc(brr_chain_create(&cfg, gg.g, &cg.c));
+    check_rc(brr_chain_open_output(cg.c, outputFile));
+    check_rc(brr_chain_run(cg.c, cfg.max_iterations, 0, nullptr, 0, nullptr));
+    check_rc(brr_chain_close_output(cg.c));
+}
+
+}  // namespace
+
+extern "C" int brr_BayesRSamplerV2(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                                   const double *X, int64_t N, int64_t M, const double *Y,
+                                   double sigma0, double v0E, double s02E, double v0G, double s02G,
+                                   const double *cva, int ncva)
+{
+    return guarded([&] {
+        BRR_REQUIRE(outputFile && X && Y && cva && N > 0 && M > 0 && ncva > 0, BRR_E_ARG, "BayesRSamplerV2: bad arguments");
+        touch_file(outputFile, sample_header(BRR_V2, N, M, 1, 0));   // file + header exist even when validation fails (:69-70,76-80)
+        check_iters(max_iterations, burn_in, thinning);
+        brr_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.kind = BRR_V2; cfg.seed = (uint64_t)(uint32_t)seed; cfg.max_iterations = max_iterations; cfg.burn_in = burn_in; cfg.thinning = thinning;
+        cfg.Y = Y; cfg.sigma0 = sigma0; cfg.v0E = v0E; cfg.s02E = s02E; cfg.v0G = v0G; cfg.s02G = s02G; cfg.cva = cva; cfg.ncva = ncva;
+        run_entry(outputFile, cfg, X, N, M);
+    });
+}
+
+extern "C" int brr_BayesRSamplerV2Groups(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                                         const double *X, int64_t N, int64_t M, const double *Y,
+                                         double sigma0, double v0E, double s02E, double v0G, double s02G,
+                                         const double *cva, int ncva, int groups, const int32_t *gAssign,
+                                         const double *fixed, int64_t F)
+{
+    return guarded([&] {
+        BRR_REQUIRE(outputFile && X && Y && cva && gAssign && N > 0 && M > 0 && ncva > 0 && groups > 0 && F >= 0, BRR_E_ARG,
+                    "BayesRSamplerV2Groups: bad arguments");
+        touch_file(outputFile, "");                                  // opened before validation, header after it (Groups:86,113)
+        check_iters(max_iterations, burn_in, thinning);
+        brr_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.kind = BRR_GROUPS; cfg.seed = (uint64_t)(uint32_t)seed; cfg.max_iterations = max_iterations; cfg.burn_in = burn_in; cfg.thinning = thinning;
+        cfg.Y = Y; cfg.sigma0 = sigma0; cfg.v0E = v0E; cfg.s02E = s02E; cfg.v0G = v0G; cfg.s02G = s02G; cfg.cva = cva; cfg.ncva = ncva;
+        cfg.groups = groups; cfg.gAssign = gAssign; cfg.fixed = fixed; cfg.F = F;
+        run_entry(outputFile, cfg, X, N, M);
+    });
+}
+
+extern "C" int brr_BRV2Grstart(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                               double mu, const double *beta, double sigmaE, const double *sigmaGG,
+                               const double *X, int64_t N, int64_t M, const double *epsilon, const double *components,
+                               double sigma0, double v0E, double s02E, double v0G, double s02G,
+                               const double *cva, int ncva, int groups, const int32_t *gAssign)
+{
+    return guarded([&] {
+        BRR_REQUIRE(outputFile && X && beta && sigmaGG && epsilon && components && cva && gAssign && N > 0 && M > 0 && ncva > 0 && groups > 0,
+                    BRR_E_ARG, "BRV2Grstart: bad arguments");
+        touch_file(outputFile, "");                                  // Grstart:84; no header is ever written
+        check_iters(max_iterations, burn_in, thinning);
+        brr_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.kind = BRR_GRSTART; cfg.seed = (uint64_t)(uint32_t)seed; cfg.max_iterations = max_iterations; cfg.burn_in = burn_in; cfg.thinning = thinning;
+        cfg.sigma0 = sigma0; cfg.v0E = v0E; cfg.s02E = s02E; cfg.v0G = v0G; cfg.s02G = s02G; cfg.cva = cva; cfg.ncva = ncva;
+        cfg.groups = groups; cfg.gAssign = gAssign;
+        cfg.mu0 = mu; cfg.beta0 = beta; cfg.sigmaE0 = sigmaE; cfg.sigmaGG0 = sigmaGG; cfg.epsilon0 = epsilon; cfg.components0 = components;
+        run_entry(outputFile, cfg, X, N, M);
+    });
+}
+
+extern "C" int brr_HorseshoeR(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                              const double *X, int64_t N, int64_t M, const double *Y,
+                              double A, double v0E, double s02E, double vL, double vT, double c2, double vC, double sC)
+{
+    return guarded([&] {
+        BRR_REQUIRE(outputFile && X && Y && N > 0 && M > 0, BRR_E_ARG, "HorseshoeR: bad arguments");
+        check_iters(max_iterations, burn_in, thinning);              // before the file is touched (HorseshoeR.cpp:119-123,274)
+        brr_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.kind = BRR_HORSESHOE; cfg.seed = (uint64_t)(uint32_t)seed; cfg.max_iterations = max_iterations; cfg.burn_in = burn_in; cfg.thinning = thinning;
+        cfg.Y = Y; cfg.v0E = v0E; cfg.s02E = s02E; cfg.A = A; cfg.vL = vL; cfg.vT = vT; cfg.c2 = c2; cfg.vC = vC; cfg.sC = sC;
+        run_entry(outputFile, cfg, X, N, M);
+    });
+}

@@ -1,0 +1,62 @@
+// Internal declarations shared by the translation units of libbayesrr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/bayesrr_b200.h"
+#include "philox.cuh"
+
+namespace brr {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+
+#define BRR_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            throw brr::Error(BRR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) +       \
+                                             " (" __FILE__ ":" + std::to_string(__LINE__) + ")");   \
+    } while (0)
+
+#define BRR_REQUIRE(cond, code, msg)                                                                \
+    do { if (!(cond)) throw brr::Error((code), (msg)); } while (0)
+
+// run `body`, translate exceptions into a return code + last-error string
+template <class F> int guarded(F &&body)
+{
+    try { body(); return BRR_OK; }
+    catch (const Error &e) { set_last_error(e.what()); return e.code; }
+    catch (const std::exception &e) { set_last_error(e.what()); return BRR_E_ARG; }
+}
+
+// throws BRR_E_CUDA unless `device` exists and is compute capability 10.x; makes it current
+void require_device(int device);
+
+constexpr int ROW_PAD = 512;   // rows per column are padded to a multiple of this (codes 0): 128-byte column stride
+
+}  // namespace brr
+
+// Genotype store (one device).  x[i, j] = a[j] + d[j] * code[i, j], code in {0,1,2}, 2 bits each, column-major.
+struct brr_geno {
+    int device = 0;
+    int64_t N = 0, M = 0;          // local rows, markers
+    int64_t Npad = 0, stride = 0;  // padded rows (multiple of ROW_PAD), bytes per column (= Npad / 4)
+    uint8_t *d_packed = nullptr;
+    // per-marker constants (device, fp64): a, d, S = sum code, Q = sum code^2, xsq = ||x||^2, csum = sum x
+    double *d_a = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Q = nullptr, *d_xsq = nullptr, *d_csum = nullptr;
+    std::vector<double> h_a, h_d, h_S, h_Q, h_xsq;
+    double n_total = 0;            // rows the statistics refer to (== N unless sharded)
+};
+
+namespace brr {
+// recompute xsq / csum (device + host mirrors) from a, d, S, Q
+void geno_finalize_stats(brr_geno *g);
+}

@@ -1,0 +1,297 @@
+// Block Gram kernels: G_b = C_b^T C_b over the raw 0/1/2 codes of the B markers of Gibbs block b
+// (markers taken in the iteration's permuted order), exact in int32.  The reference has no such
+// operation: it is what replaces the marker-to-marker dependency through the N-vector residual
+// (reference src/BayesRv2.cpp:191 -> :243) by a B x B correction ("block-Gram identity").
+//
+//   gram_tc_kernel   : tcgen05.mma kind::i8, accumulators in TMEM, operands unpacked 2-bit -> int8 into the
+//                      canonical K-major (no-swizzle) shared-memory layout, packed columns staged by
+//                      cp.async.bulk (TMA) with mbarrier completion.  One CTA per block.
+//   gram_dp4a_kernel : CUDA-core reference of the same integers (validation / debugging only).
+#include "common.cuh"
+
+namespace brr {
+
+constexpr int GRAM_KC = 512;                       // rows (K) per pipeline stage
+constexpr int GRAM_STAGE_ROW = GRAM_KC / 4 + 16;   // bytes per staged packed column (padded: conflict-free 128-bit reads)
+constexpr int GRAM_TILE_BYTES = 128 * GRAM_KC;     // int8 operand tile: 128 marker rows x KC
+constexpr int GRAM_SBO = (GRAM_KC / 16) * 128;     // byte stride between 8-marker groups
+constexpr int GRAM_LBO = 128;                      // byte stride between K-adjacent 8x16B core matrices
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait (~2 s): a lost completion must not hang the GPU; the result is then wrong and the parity tests say so
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) { __trap(); }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (tcgen05): start address, LBO, SBO in 16-byte units, version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(GRAM_LBO >> 4) << 16) | ((uint64_t)(GRAM_SBO >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// 16 2-bit codes (one packed word) -> 16 bytes
+__device__ __forceinline__ uint4 expand16(uint32_t w)
+{
+    uint4 r;
+    uint32_t b;
+    b = w & 0xFFu;          r.x = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+    b = (w >> 8) & 0xFFu;   r.y = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+    b = (w >> 16) & 0xFFu;  r.z = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+    b = w >> 24;            r.w = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+    return r;
+}
+
+template <int B>
+__global__ void __launch_bounds__(256, 1)
+gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
+               const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G)
+{
+    static_assert(B == 32 || B == 64 || B == 128, "block size");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *tile0 = smem;                                  // 2 x 64 KB operand tiles
+    uint8_t *stage0 = smem + 2 * GRAM_TILE_BYTES;           // 2 x B x GRAM_STAGE_ROW staged packed columns
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + 2 * B * GRAM_STAGE_ROW);   // full[2], free[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    int32_t *cols = reinterpret_cast<int32_t *>(tmem_slot + 2);                        // B marker ids
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t blk = blockIdx.x;
+    uint64_t *full = bars, *freeb = bars + 2;
+
+    if (tid < B) {
+        const int64_t o = blk * B + tid;
+        cols[tid] = o < n_order ? order[o] : -1;
+    }
+    // zero both operand tiles (rows of padding markers and rows >= B must read as 0) and both stages
+    for (int i = tid; i < (2 * GRAM_TILE_BYTES + 2 * B * GRAM_STAGE_ROW) / 16; i += 256)
+        reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&freeb[0], 1); mbar_init(&freeb[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {   // TMEM: 128 lanes x 128 int32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    const int nchunks = (int)(Npad / GRAM_KC);
+    int nvalid = 0;
+    for (int c = 0; c < B; ++c) nvalid += cols[c] >= 0;
+
+    auto issue_loads = [&](int chunk) {   // called by threads < B after thread 0's expect_tx; one 128-byte bulk copy per marker
+        const int s = chunk & 1;
+        if (tid == 0) mbar_expect_tx(&full[s], (uint32_t)nvalid * (GRAM_KC / 4));
+        if (tid < B && cols[tid] >= 0)
+            bulk_g2s(stage0 + (s * B + tid) * GRAM_STAGE_ROW, packed + (int64_t)cols[tid] * stride + (int64_t)chunk * (GRAM_KC / 4),
+                     GRAM_KC / 4, &full[s]);
+    };
+    if (nvalid == 0) {   // nothing to do but keep the protocol simple: write zeros
+        for (int i = tid; i < B * B; i += 256) G[blk * B * B + i] = 0;
+    } else {
+        issue_loads(0);
+        if (nchunks > 1) issue_loads(1);
+        // instruction descriptor: D = S32, A = B = unsigned 8-bit, both K-major, N = B, M = 128
+        constexpr uint32_t idesc = (2u << 4) | ((uint32_t)(B >> 3) << 17) | ((128u >> 4) << 24);
+        for (int i = 0; i < nchunks; ++i) {
+            const int s = i & 1;
+            mbar_wait(&full[s], (uint32_t)((i >> 1) & 1));
+            if (i >= 2) mbar_wait(&freeb[s], (uint32_t)(((i >> 1) - 1) & 1));
+            uint8_t *tile = tile0 + s * GRAM_TILE_BYTES;
+            const uint8_t *stage = stage0 + s * B * GRAM_STAGE_ROW;
+            // unpack: item = (v, c): 64 rows of marker c -> four 16-byte core-matrix rows
+            for (int item = tid; item < B * (GRAM_KC / 64); item += 256) {
+                const int c = item % B, v = item / B;
+                const uint4 q = *reinterpret_cast<const uint4 *>(stage + c * GRAM_STAGE_ROW + v * 16);
+                uint8_t *dst = tile + (c >> 3) * GRAM_SBO + (c & 7) * 16 + (v * 4) * GRAM_LBO;
+                *reinterpret_cast<uint4 *>(dst) = expand16(q.x);
+                *reinterpret_cast<uint4 *>(dst + GRAM_LBO) = expand16(q.y);
+                *reinterpret_cast<uint4 *>(dst + 2 * GRAM_LBO) = expand16(q.z);
+                *reinterpret_cast<uint4 *>(dst + 3 * GRAM_LBO) = expand16(q.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncthreads();
+            if (i + 2 < nchunks) issue_loads(i + 2);                        // stage s is free again
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(tile);
+#pragma unroll 4
+                for (int kk = 0; kk < GRAM_KC / 32; ++kk) {
+                    const uint64_t da = umma_desc(base + kk * 2 * GRAM_LBO);
+                    const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(da), "l"(da), "r"(idesc), "r"(acc) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(smem_u32(&freeb[s])) : "memory");
+            }
+        }
+        {   // all MMAs done?
+            const int last = nchunks - 1;
+            mbar_wait(&freeb[last & 1], (uint32_t)((last >> 1) & 1));
+            if (nchunks > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1)); }
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: TMEM lane = marker row i, column = marker j
+        if (warp < 4) {
+            const int row = warp * 32 + (tid & 31);
+#pragma unroll
+            for (int c0 = 0; c0 < B; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < B) {
+                    int4 *dst = reinterpret_cast<int4 *>(G + (blk * B + row) * B + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
+// ---- CUDA-core reference: 8 x 8 register tile per thread, dp4a over int8-expanded codes.
+template <int B>
+__global__ void __launch_bounds__(256) gram_dp4a_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
+                                                        const int32_t *__restrict__ order, int64_t n_order,
+                                                        int32_t *__restrict__ G)
+{
+    constexpr int KR = 64;                     // rows per smem tile
+    constexpr int TS = (B + 15) / 16;          // per-thread tile side: 256 threads = 16 x 16
+    __shared__ uint32_t tile[B][KR / 4 + 1];   // int8 x 4 words
+    __shared__ int32_t cols[B];
+    const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+    const int64_t blk = blockIdx.x;
+    if (tid < B) { const int64_t o = blk * B + tid; cols[tid] = o < n_order ? order[o] : -1; }
+    __syncthreads();
+    int acc[TS][TS];
+#pragma unroll
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b) acc[a][b] = 0;
+    for (int64_t r0 = 0; r0 < Npad; r0 += KR) {
+        for (int item = tid; item < B * (KR / 16); item += 256) {
+            const int c = item / (KR / 16), w = item % (KR / 16);
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (cols[c] >= 0) e = expand16(*reinterpret_cast<const uint32_t *>(packed + (int64_t)cols[c] * stride + r0 / 4 + w * 4));
+            tile[c][w * 4] = e.x; tile[c][w * 4 + 1] = e.y; tile[c][w * 4 + 2] = e.z; tile[c][w * 4 + 3] = e.w;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < KR / 4; ++k) {
+            uint32_t av[TS], bv[TS];
+#pragma unroll
+            for (int a = 0; a < TS; ++a) { av[a] = tile[ti + 16 * a][k]; bv[a] = tile[tj + 16 * a][k]; }
+#pragma unroll
+            for (int a = 0; a < TS; ++a)
+#pragma unroll
+                for (int b = 0; b < TS; ++b) acc[a][b] = __dp4a((int)av[a], (int)bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b) {
+            const int i = ti + 16 * a, j = tj + 16 * b;
+            if (i < B && j < B) G[(blk * B + i) * B + j] = acc[a][b];
+        }
+}
+
+template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * B * GRAM_STAGE_ROW + 4 * 8 + 8 + B * 4 + 64; }
+
+// launch on `stream`; G must hold nblocks * B * B int32
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, cudaStream_t stream)
+{
+    const int64_t nb = (n_order + B - 1) / B;
+    if (nb == 0) return;
+    BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
+#define BRR_GRAM_CASE(BB)                                                                                                   \
+    if (B == BB) {                                                                                                          \
+        if (impl == 0) {                                                                                                    \
+            static bool attr_set = false;                                                                                   \
+            if (!attr_set) {                                                                                                \
+                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
+                attr_set = true;                                                                                            \
+            }                                                                                                               \
+            gram_tc_kernel<BB><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G); \
+        } else {                                                                                                            \
+            gram_dp4a_kernel<BB><<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G);      \
+        }                                                                                                                   \
+    }
+    BRR_GRAM_CASE(32) BRR_GRAM_CASE(64) BRR_GRAM_CASE(128)
+#undef BRR_GRAM_CASE
+    BRR_CUDA(cudaGetLastError());
+}
+
+}  // namespace brr
+
+using namespace brr;
+
+extern "C" int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
+                               int32_t *G_out, double *ms)
+{
+    return guarded([&] {
+        BRR_REQUIRE(g && order && G_out && n_order > 0, BRR_E_ARG, "bad arguments");
+        BRR_CUDA(cudaSetDevice(g->device));
+        for (int64_t i = 0; i < n_order; ++i)
+            BRR_REQUIRE(order[i] >= -1 && order[i] < g->M, BRR_E_ARG, "order entry out of range");
+        const int64_t nb = (n_order + block - 1) / block;
+        int32_t *d_order = nullptr, *d_G = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        try {
+            BRR_CUDA(cudaMalloc(&d_order, n_order * 4));
+            BRR_CUDA(cudaMalloc(&d_G, (size_t)nb * block * block * 4));
+            BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
+            BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
+            launch_gram(g, d_order, n_order, block, impl, d_G, 0);   // warm-up (module load, attribute)
+            BRR_CUDA(cudaEventRecord(e0));
+            launch_gram(g, d_order, n_order, block, impl, d_G, 0);
+            BRR_CUDA(cudaEventRecord(e1));
+            BRR_CUDA(cudaEventSynchronize(e1));
+            float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;
+            BRR_CUDA(cudaMemcpy(G_out, d_G, (size_t)nb * block * block * 4, cudaMemcpyDeviceToHost));
+        } catch (...) { cudaFree(d_order); cudaFree(d_G); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
+        cudaFree(d_order); cudaFree(d_G); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    });
+}

@@ -1,0 +1,77 @@
+// Parameters of the persistent per-iteration sweep kernel (sweep.cu) and of the hyper-parameter kernels (hyper.cu).
+#pragma once
+#include "common.cuh"
+
+namespace brr {
+
+constexpr int SWEEP_THREADS = 256;
+constexpr int KMAX = 16;          // mixture components supported by the in-block sampler
+
+// Scalars of the chain that live on the device between kernels.
+struct IterScalars {
+    double mu;        // intercept of the iteration whose sweep ran last
+    double mu_next;   // intercept drawn for the next iteration (reference src/BayesRv2.cpp:178)
+    double shift;     // mu - mu_next: added to every residual when the next sweep loads it (:177,:179)
+    double eps_sum;   // sum of residuals after the shift (kept analytically inside the sweep)
+    double eps_sq;    // ||eps||^2 after the last sweep
+    double sigmaE, sigmaF;
+    double tau, c2, eta, eta_next;   // horseshoe (eta_next: drawn for the next iteration, reference HorseshoeR.cpp:217)
+    double beta_sq;        // ||beta||^2 after the last sweep
+    int64_t it_done;       // iterations completed
+};
+
+struct SweepParams {
+    // genotypes (local rows)
+    const uint8_t *packed; int64_t stride; int64_t N;
+    const double *colA, *colD, *colS, *colXsq, *colCsum;
+    double n_total;
+    // iteration inputs
+    const int32_t *perm;          // M markers in visiting order
+    const int32_t *gram;          // nb x B x B int32 (codes), rows/cols in visiting order
+    int64_t M; int nb;
+    int64_t it;
+    // chain state
+    double *eps;                  // Npad residuals (local rows)
+    double *beta;                 // M
+    double *comp;                 // M (component ids stored as doubles like the reference's sample row)
+    IterScalars *sc;
+    // mixture model (kind 0)
+    int K, G;
+    const int32_t *gAssign;       // M or null (single group)
+    const double *cva;            // G x (K-1) column-major
+    const double *sigmaG;         // G
+    const double *pi;             // G x K row-major
+    double *vcount;               // G x K  (output: component counts of this sweep)
+    double *betaAcum;             // G      (output: sum of squared non-zero draws per group, sweep order)
+    // horseshoe (kind 1)
+    const double *lambda;         // M
+    // draws
+    PhiloxKey key;
+    const double *tbl_u, *tbl_z;  // replay tables of this iteration (M each) or null
+    // fixed effects (Groups)
+    int F; const double *fixed;   // N x F column-major (local rows), or null
+    const int32_t *fixperm;       // F
+    const double *fixG;           // F x F Gram of the fixed columns (fp64)
+    double *alpha;                // F
+    const double *tbl_fix_z;      // F or null
+    // grid protocol
+    unsigned *arrive, *go;        // zeroed before launch
+    int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
+    double *partials;             // nW x PS
+    double *bcast;                // 3 x PS: delta, a*delta, d*delta (visiting order within the block)
+    double *fin;                  // nW x 2: sum eps, sum eps^2 over the worker's rows
+    int nW; int PS;
+    const int32_t *unit0;         // nW + 1: first 64-row unit of every worker
+    int seg_bytes;                // bytes reserved per staged column segment (max units * 16)
+};
+
+// Geometry helpers shared by host and device
+struct SweepGeom { int B, TW, nW, seg_bytes; size_t smem_bytes; };
+
+void launch_sweep(int kind, int B, int TW, const SweepParams &p, size_t smem, cudaStream_t stream);
+size_t sweep_smem_bytes(int kind, int B, int K, int G, int F, int seg_bytes);
+int sweep_max_coresident(int kind, int B, int TW, size_t smem);
+
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, cudaStream_t stream);
+
+}  // namespace brr

@@ -1,0 +1,149 @@
+// Sample sink: queue-backed CSV writer with the observable behaviour of the reference's
+// moodycamel::ConcurrentQueue<Eigen::VectorXd> + ofstream pair (reference src/BayesRv2.cpp:62,72,260-267,282-289;
+// same pattern in the other three samplers): the sampler thread enqueue()s one row per kept iteration, a consumer
+// thread try_dequeue()s and writes `row.transpose().format(CommaInitFmt)` -- "%g"-formatted numbers (ostream
+// precision 6) joined by ", " -- plus '\n'.  One producer, one consumer, so a bounded ring replaces the MPMC queue.
+// Deliberate differences: the stop flag is atomic and the consumer DRAINS the queue after stop,
+// so every kept row reaches the file, in order, for all four samplers.
+#include "common.cuh"
+#include "writer.h"
+#include <cstdio>
+#include <cstring>
+
+namespace brr {
+
+RowQueue::RowQueue(size_t capacity) : slots_(capacity + 1) {}
+
+bool RowQueue::try_enqueue(std::vector<double> &&row)
+{
+    const size_t h = head_.load(std::memory_order_relaxed), n = (h + 1) % slots_.size();
+    if (n == tail_.load(std::memory_order_acquire)) return false;   // full
+    slots_[h] = std::move(row);
+    head_.store(n, std::memory_order_release);
+    return true;
+}
+void RowQueue::enqueue(std::vector<double> &&row)
+{
+    std::vector<double> r = std::move(row);
+    while (true) {
+        const size_t h = head_.load(std::memory_order_relaxed), n = (h + 1) % slots_.size();
+        if (n != tail_.load(std::memory_order_acquire)) { slots_[h] = std::move(r); head_.store(n, std::memory_order_release); return; }
+        std::this_thread::yield();
+    }
+}
+bool RowQueue::try_dequeue(std::vector<double> &row)
+{
+    const size_t t = tail_.load(std::memory_order_relaxed);
+    if (t == head_.load(std::memory_order_acquire)) return false;   // empty
+    row = std::move(slots_[t]);
+    tail_.store((t + 1) % slots_.size(), std::memory_order_release);
+    return true;
+}
+
+static void put_indexed(std::string &s, const char *name, long i, const char *tail)
+{
+    char t[64];
+    snprintf(t, sizeof t, "%s[%ld]%s", name, i, tail);
+    s += t;
+}
+
+// Header text per sampler: src/BayesRv2.cpp:16-37, src/BayesRv2Groups.cpp:25-54, src/HorseshoeR.cpp:279-291 (trailing comma).
+// BRV2Grstart defines a header writer (src/BRv2Grstart.cpp:26-50) but never calls it: its file has no header line.
+std::string sample_header(int kind, int64_t N, int64_t M, int G, int64_t F)
+{
+    std::string s;
+    if (kind == BRR_GRSTART) return s;
+    s.reserve((size_t)(2 * M + N) * 14);
+    s += "iteration,"; s += "mu,";
+    for (int64_t i = 0; i < M; ++i) put_indexed(s, "beta", i + 1, ",");
+    if (kind == BRR_V2) {
+        s += "sigmaE,"; s += "sigmaG,";
+        for (int64_t i = 0; i < M; ++i) put_indexed(s, "comp", i + 1, ",");
+        for (int64_t i = 0; i < N - 1; ++i) put_indexed(s, "epsilon", i + 1, ",");
+        put_indexed(s, "epsilon", N, "");
+    } else if (kind == BRR_GROUPS) {
+        s += "sigmaE,";
+        for (int64_t i = 0; i < M; ++i) put_indexed(s, "comp", i + 1, ",");
+        for (int i = 0; i < G; ++i) put_indexed(s, "sigmaG", i + 1, ",");
+        for (int64_t i = 0; i < N - 1; ++i) put_indexed(s, "epsilon", i + 1, ",");
+        put_indexed(s, "epsilon", N, ",");
+        for (int64_t i = 0; i < F; ++i) put_indexed(s, "alpha", i + 1, ",");
+        s += "sigmaF";
+    } else {
+        s += "sigmaE,"; s += "tau,";
+        for (int64_t i = 0; i < M; ++i) put_indexed(s, "lambda", i + 1, ",");
+        for (int64_t i = 0; i < N; ++i) put_indexed(s, "epsilon", i + 1, ",");
+    }
+    s += "\n";
+    return s;
+}
+
+void format_row(const double *row, size_t len, std::string &out)
+{
+    out.clear();
+    out.reserve(len * 12 + 2);
+    char t[40];
+    for (size_t i = 0; i < len; ++i) {
+        const int n = snprintf(t, sizeof t, "%g", row[i]);
+        if (i) out.append(", ", 2);
+        out.append(t, (size_t)n);
+    }
+    out.push_back('\n');
+}
+
+SampleWriter::SampleWriter(const std::string &path, const std::string &header, bool write_header_now)
+    : q_(8), header_(header)
+{
+    f_ = fopen(path.c_str(), "w");   // truncates like ofstream::open (src/BayesRv2.cpp:69)
+    if (!f_) throw Error(BRR_E_IO, "cannot open output file '" + path + "'");
+    if (write_header_now && !header_.empty()) { fwrite(header_.data(), 1, header_.size(), f_); header_.clear(); }
+}
+void SampleWriter::start()
+{
+    if (running_) return;
+    running_ = true;
+    stop_.store(false);
+    th_ = std::thread([this] {
+        if (!header_.empty()) { fwrite(header_.data(), 1, header_.size(), f_); header_.clear(); }
+        std::vector<double> row; std::string text;
+        while (true) {
+            if (q_.try_dequeue(row)) {
+                format_row(row.data(), row.size(), text);
+                if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
+                rows_written_.fetch_add(1);
+            } else if (stop_.load(std::memory_order_acquire)) {
+                if (!q_.try_dequeue(row)) break;          // drained
+                format_row(row.data(), row.size(), text);
+                if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
+                rows_written_.fetch_add(1);
+            } else {
+                std::this_thread::yield();
+            }
+        }
+    });
+}
+void SampleWriter::enqueue(const double *row, size_t len)
+{
+    if (!running_) start();
+    q_.enqueue(std::vector<double>(row, row + len));
+}
+void SampleWriter::finish()
+{
+    if (running_) {
+        stop_.store(true, std::memory_order_release);
+        th_.join();
+        running_ = false;
+    }
+    if (f_) {
+        if (!header_.empty()) { fwrite(header_.data(), 1, header_.size(), f_); header_.clear(); }
+        if (fflush(f_) != 0) io_error_.store(true);
+        fclose(f_); f_ = nullptr;
+    }
+    if (io_error_.load()) throw Error(BRR_E_IO, "write to the sample file failed");
+}
+SampleWriter::~SampleWriter()
+{
+    try { finish(); } catch (...) { }
+}
+
+}  // namespace brr

@@ -1,0 +1,169 @@
+/*
+ * bayesrr_b200.h -- C ABI of the B200-native BayesR / BayesRR / Horseshoe Gibbs sampler.
+ *
+ * Plain pointers and sizes only (no torch / Eigen / Rcpp types).  Every entry point returns 0 on
+ * success or a BRR_E_* code; brr_last_error() returns the message of the last failure on the calling
+ * thread.  There is no CPU fallback: every call that computes requires an sm_100 device and fails
+ * with BRR_E_CUDA otherwise.
+ *
+ * Reference interface replaced (file:line relative to the reference repository):
+ *   brr_BayesRSamplerV2        <- void BayesRSamplerV2(...)        src/BayesRv2.cpp:60        (glue src/RcppExports.cpp:39-59)
+ *   brr_BayesRSamplerV2Groups  <- void BayesRSamplerV2Groups(...)  src/BayesRv2Groups.cpp:75  (glue src/RcppExports.cpp:61-84)
+ *   brr_BRV2Grstart            <- void BRV2Grstart(...)            src/BRv2Grstart.cpp:77     (glue src/RcppExports.cpp:10-37)
+ *   brr_HorseshoeR             <- void HorseshoeR(...)             src/HorseshoeR.cpp:109     (glue src/RcppExports.cpp:86-108)
+ * Arguments keep the reference's order and meaning; every Eigen matrix/vector becomes (pointer, sizes),
+ * column-major like Eigen.  Results are delivered through `outputFile` exactly like the reference
+ * (header + one ", "-separated row per kept iteration, src/BayesRv2.cpp:16-37,72,260-267).
+ * INTEGRATION.md shows the Rcpp-side binding a maintainer adds.
+ */
+#ifndef BAYESRR_B200_H
+#define BAYESRR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    BRR_OK = 0,
+    BRR_E_ITER = 1,     /* max_iterations < burn_in || max_iterations < 1 || burn_in < 1 (src/BayesRv2.cpp:76-80);
+                           the output file has been truncated (and, for V2, the header written) like the reference */
+    BRR_E_ARG = 2,      /* invalid argument (null pointer, size mismatch, thinning < 1, ...) */
+    BRR_E_GENO = 3,     /* a column of X is not representable as a + d*code with code in {0,1,2} */
+    BRR_E_CUDA = 4,     /* CUDA failure or no sm_100 device: there is no CPU fallback */
+    BRR_E_IO = 5,       /* output file cannot be opened / written */
+    BRR_E_SIZE = 6      /* problem does not fit this build's limits (K, rows per device) */
+};
+enum { BRR_V2 = 0, BRR_GROUPS = 1, BRR_GRSTART = 2, BRR_HORSESHOE = 3 };
+
+const char *brr_last_error(void);
+int brr_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * The four reference entry points.  X is N x M column-major fp64 (what Rcpp hands over as
+ * Eigen::MatrixXd); each column must take at most three equally spaced values (a standardised
+ * 0/1/2 genotype column), see brr_geno_from_dense.
+ * ------------------------------------------------------------------------------------------------ */
+int brr_BayesRSamplerV2(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                        const double *X, int64_t N, int64_t M, const double *Y,
+                        double sigma0, double v0E, double s02E, double v0G, double s02G,
+                        const double *cva, int ncva);
+
+/* cva: groups x ncva column-major (Eigen::MatrixXd); gAssign: M zero-based group ids; fixed: N x F column-major (F may be 0) */
+int brr_BayesRSamplerV2Groups(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                              const double *X, int64_t N, int64_t M, const double *Y,
+                              double sigma0, double v0E, double s02E, double v0G, double s02G,
+                              const double *cva, int ncva, int groups, const int32_t *gAssign,
+                              const double *fixed, int64_t F);
+
+/* beta: M; sigmaGG: groups; epsilon: N; components: M doubles (as in the reference, src/BRv2Grstart.cpp:77) */
+int brr_BRV2Grstart(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                    double mu, const double *beta, double sigmaE, const double *sigmaGG,
+                    const double *X, int64_t N, int64_t M, const double *epsilon, const double *components,
+                    double sigma0, double v0E, double s02E, double v0G, double s02G,
+                    const double *cva, int ncva, int groups, const int32_t *gAssign);
+
+int brr_HorseshoeR(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
+                   const double *X, int64_t N, int64_t M, const double *Y,
+                   double A, double v0E, double s02E, double vL, double vT, double c2, double vC, double sC);
+
+/* ------------------------------------------------------------------------------------------------
+ * Genotype storage / packing layer: 2-bit codes, column-major, 16-byte aligned column stride,
+ * resident in HBM; per-SNP affine map x = a + d*code (a = -mean/sd, d = 1/sd for scale()d columns).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct brr_geno brr_geno;
+
+/* Pack a dense column-major fp64 matrix (host memory).  Fails with BRR_E_GENO when a column has more
+ * than three distinct values or they are not equally spaced (relative tolerance 1e-9). */
+int brr_geno_from_dense(const double *X, int64_t N, int64_t M, int device, brr_geno **out);
+/* Adopt host 2-bit codes: column j starts at packed + j*col_stride_bytes, individual i is bits
+ * 2*(i%4).. of byte i/4, code 3 is rejected (missing data is not a concept of the reference).
+ * mean/sd NULL -> computed from the codes (sd with the N-1 denominator, like R scale()).       */
+int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_bytes, int64_t N, int64_t M,
+                         const double *mean, const double *sd, int device, brr_geno **out);
+/* Device-side synthetic generator: g_ij ~ Binomial(2, p_j), p_j ~ U(0.05, 0.5), standardised.
+ * Row sharding: this store holds rows [row0, row0+N) of a virtual N_total-row matrix (statistics are
+ * computed over the local rows only unless brr_geno_set_stats is called).                       */
+int brr_geno_synthetic(int64_t N, int64_t M, uint64_t seed, int64_t row0, int device, brr_geno **out);
+int brr_geno_dims(const brr_geno *g, int64_t *N, int64_t *M, int64_t *col_stride_bytes);
+/* host copies of the per-SNP statistics (any pointer may be NULL): code mean, code sd, a, d, ||x||^2 */
+int brr_geno_stats(const brr_geno *g, double *mean, double *sd, double *a, double *d, double *xsq);
+/* host copy of the packed codes (M * col_stride_bytes) */
+int brr_geno_codes(const brr_geno *g, uint8_t *packed_out);
+/* y = X * b for host vectors b (M) -> y (N): builds phenotypes for configurations whose dense X cannot exist */
+int brr_geno_matvec(const brr_geno *g, const double *b, double *y);
+void brr_geno_free(brr_geno *g);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chain objects: what the four entry points are built from; used directly by tests, the benchmark and
+ * configurations that cannot pass through a dense X.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct brr_chain brr_chain;
+
+typedef struct brr_config {
+    int kind;                       /* BRR_V2 ... BRR_HORSESHOE */
+    uint64_t seed;                  /* Philox key (the reference ignores its seed) */
+    int max_iterations, burn_in, thinning;
+    const double *Y;                /* N (not used by BRR_GRSTART) */
+    double sigma0, v0E, s02E, v0G, s02G;
+    const double *cva; int ncva;    /* V2: ncva values; Groups/Grstart: groups x ncva column-major */
+    int groups; const int32_t *gAssign;
+    const double *fixed; int64_t F; /* Groups only */
+    const double *pi_init;          /* V2 only, K = ncva+1 values; NULL -> {0.5, 0.5*cva/sum(cva)} */
+    /* BRR_GRSTART state (src/BRv2Grstart.cpp:61-67) */
+    double mu0; const double *beta0; double sigmaE0; const double *sigmaGG0;
+    const double *epsilon0; const double *components0;
+    /* BRR_HORSESHOE (src/HorseshoeR.cpp:109) */
+    double A, vL, vT, c2, vC, sC;
+    /* engine options; 0 = default */
+    int block;                      /* markers per Gibbs block: 32, 64 or 128 (default 128) */
+    int gram_impl;                  /* 0 = tcgen05 int8 tensor cores, 1 = dp4a CUDA cores (validation) */
+    int workers;                    /* worker CTAs of the persistent sweep kernel (default: SMs - 1) */
+    int speculate;                  /* reserved */
+} brr_config;
+
+/* Draw-replay tables (host memory, copied at set time).  Layout per iteration t in [0, n_iter):
+ *   perm[t*M + j]   marker visited at sweep position j
+ *   mark_u[t*M + j] uniform used at position j;  mark_z[t*M + j] standard normal (NaN where unused)
+ *   mu_z[t]; gam[t*n_gam + slot] unit-scale gamma variates; fix_z[t*F + j], fixperm[t*F + j];
+ *   hs_nu[t*M + marker], hs_lam[t*M + marker];  init_u / init_g: draws made before iteration 0.
+ * Slot numbering per sampler is documented in DESIGN.md.                                            */
+typedef struct brr_replay {
+    int64_t n_iter, M, F, n_gam, n_init_u, n_init_g;
+    const double *mark_u, *mark_z, *mu_z, *gam, *fix_z, *hs_nu, *hs_lam, *init_u, *init_g;
+    const int32_t *perm, *fixperm;
+} brr_replay;
+
+int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **out);
+int brr_chain_set_replay(brr_chain *c, const brr_replay *r);
+/* Append sample rows to `path` exactly like the reference writer (header written immediately). */
+int brr_chain_open_output(brr_chain *c, const char *path);
+int64_t brr_chain_row_len(const brr_chain *c);
+/* Run n_iter further iterations.  rows (may be NULL): receives up to max_rows sample rows (reference row
+ * layout) for kept iterations, or for every iteration when emit_all != 0; *n_rows = rows produced. */
+int brr_chain_run(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows);
+/* mixture proportions after the last completed iteration: groups x K row-major (V2: K values) */
+int brr_chain_get_pi(brr_chain *c, double *pi);
+/* Horseshoe: eta, tau, c2 after the last completed iteration */
+int brr_chain_get_hyper(brr_chain *c, double *eta_tau_c2);
+/* device time (ms, CUDA events on the chain's stream) and kernel launches of the last brr_chain_run */
+int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches);
+/* flush the writer and close the output file */
+int brr_chain_close_output(brr_chain *c);
+void brr_chain_destroy(brr_chain *c);
+
+/* Stand-alone kernels exposed for parity tests and roofline measurement.
+ * gram: G[b][i][j] = sum_n code[n, order[b*B+i]] * code[n, order[b*B+j]]  (int32, nb x B x B; order index -1 = padding) */
+int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
+                    int32_t *G_out, double *ms);
+/* r[j] = sum_n x[n, j] * eps[n] for every marker (host eps N -> host r M), the streaming X^T eps kernel */
+int brr_xt_eps(const brr_geno *g, const double *eps, double *r, double *ms);
+/* counter-based draws exactly as the device code makes them (for generator parity tests) */
+int brr_draws_sample(uint64_t seed, int stream, int64_t it, int64_t idx0, int64_t n, int kind /*0 u, 1 z, 2 gamma*/,
+                     double shape, double *out);
+int brr_shuffle_host(uint64_t seed, int stream, int64_t it, int32_t *order, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the library builds, loads and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bayesrr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(brr_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_four_reference_entry_points():
+    syms = declared_symbols()
+    for name in ("brr_BayesRSamplerV2", "brr_BayesRSamplerV2Groups", "brr_BRV2Grstart", "brr_HorseshoeR"):
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol(brr):
+    lib = ctypes.CDLL(brr.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.brr_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device(brr):
+    """Without a GPU every computing call must fail loudly with BRR_E_CUDA (never a silent CPU path)."""
+    import numpy as np
+    import pytest
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_dense(np.zeros((8, 2)))
+    assert e.value.code == brr.E_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_references_the_oracle():
+    """The shipped package must not import, include or link anything under oracle/."""
+    pkg = os.path.join(ROOT, "bayesrrcpp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "pyoracle" not in text and "oracle/" not in text, os.path.join(dirpath, f)
+                assert "liboracle" not in text and "orc_" not in text, os.path.join(dirpath, f)
+
+
+def test_entry_point_iteration_validation_matches_reference(brr, tmp_path):
+    """src/BayesRv2.cpp:69-80: V2 truncates the file and writes the header before rejecting the iteration arguments;
+    HorseshoeR (src/HorseshoeR.cpp:119-123) returns before touching the file.  Validation precedes any device work."""
+    import numpy as np
+    X = np.zeros((8, 3)); Y = np.zeros(8)
+    out = tmp_path / "v2.csv"
+    try:
+        brr.BayesRSamplerV2(str(out), 1, 5, 10, 1, X, Y, 0.01, 1e-4, 1e-3, 1e-4, 1e-3, [1e-4, 1e-3, 1e-2])
+        raise AssertionError("expected an error")
+    except brr.BayesRRError as e:
+        assert e.code == brr.E_ITER
+    text = out.read_text()
+    assert text.startswith("iteration,mu,beta[1],beta[2],beta[3],sigmaE,sigmaG,comp[1],") and text.endswith("epsilon[8]\n")
+    out2 = tmp_path / "hs.csv"
+    try:
+        brr.HorseshoeR(str(out2), 1, 5, 0, 1, X, Y, 0.1, 1e-3, 1e-3, 1, 1, 1, 10, 10)
+        raise AssertionError("expected an error")
+    except brr.BayesRRError as e:
+        assert e.code == brr.E_ITER
+    assert not out2.exists()
