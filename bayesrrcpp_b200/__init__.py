@@ -262,6 +262,21 @@ class Chain:
         _check(lib().brr_chain_last_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def kernel_ms(self):
+        out = np.zeros(3)
+        _check(lib().brr_chain_kernel_ms(self._h, _p(out)))
+        return dict(gram=out[0], sweep=out[1], hyper=out[2])
+
+    def sweep_profile(self):
+        o = np.zeros(8)
+        _check(lib().brr_chain_sweep_profile(self._h, _p(o)))
+        return dict(wait=o[0], reduce=o[1], serial_pass=o[2], publish=o[3], windows=o[4], full_steps=o[5], blocks=o[6])
+
+    def geometry(self):
+        b, w, r, s = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _check(lib().brr_chain_geometry(self._h, C.byref(b), C.byref(w), C.byref(r), C.byref(s)))
+        return dict(block=b.value, workers=w.value, rows_per_worker_max=r.value, smem_bytes=s.value)
+
     def close(self):
         if self._h:
             lib().brr_chain_destroy(self._h)

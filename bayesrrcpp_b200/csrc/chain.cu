@@ -63,6 +63,7 @@ struct brr_chain {
     DevBuf<IterScalars> sc;
     DevBuf<unsigned> sync;
     DevBuf<int> abort_flag;
+    DevBuf<long long> prof;
     PinBuf<int32_t> h_perm[PERM_RING]; DevBuf<int32_t> d_perm[PERM_RING]; cudaEvent_t perm_free[PERM_RING] = {}; bool perm_used[PERM_RING] = {};
     std::vector<int32_t> markerI, fixedI;
     // replay
@@ -75,6 +76,8 @@ struct brr_chain {
     int64_t it = 0; bool initialised = false;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0; int64_t last_launches = 0;
+    std::vector<cudaEvent_t> kev;            // 4 events per iteration: gram | sweep | hyper boundaries
+    double last_kernel_ms[3] = {0, 0, 0};
 
     int64_t row_len() const
     {
@@ -90,6 +93,7 @@ struct brr_chain {
         if (g) cudaSetDevice(g->device);
         for (auto &e : perm_free) if (e) cudaEventDestroy(e);
         for (auto &s : snaps) if (s.ready) cudaEventDestroy(s.ready);
+        for (auto &e : kev) if (e) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -238,6 +242,7 @@ void chain_init(brr_chain *c)
     c->fin.alloc((size_t)2 * c->nW); c->fin.zero();
     c->sync.alloc(2);
     c->abort_flag.alloc(1); c->abort_flag.zero();
+    c->prof.alloc(8); c->prof.zero();
     c->gram.alloc((size_t)c->nb * c->B * c->B);
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
@@ -305,6 +310,8 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
     const int kk = c->kind == BRR_HORSESHOE ? 1 : 0;
     int64_t launches = 0;
+    c->prof.zero(c->stream);
+    while (c->kev.size() < (size_t)4 * n_iter) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
     BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
     for (int n = 0; n < n_iter; ++n) {
         const int64_t it = c->it;
@@ -324,8 +331,10 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         if (F > 0) BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p + fo, hp + fo, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream));
         c->perm_used[slot] = true;
 
+        BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
         launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
         BRR_CUDA(cudaMemsetAsync(c->sync.p, 0, 2 * sizeof(unsigned), c->stream));
+        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 
         SweepParams p; memset(&p, 0, sizeof p);
         const brr_geno *g = c->g;
@@ -340,9 +349,10 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
         p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
-        p.arrive = c->sync.p; p.go = c->sync.p + 1; p.abort_flag = c->abort_flag.p; p.partials = c->partials.p; p.bcast = c->bcast.p; p.fin = c->fin.p;
+        p.arrive = c->sync.p; p.go = c->sync.p + 1; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.partials = c->partials.p; p.bcast = c->bcast.p; p.fin = c->fin.p;
         p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
+        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
         BRR_CUDA(cudaEventRecord(c->perm_free[slot], c->stream));
 
         HyperParams h; memset(&h, 0, sizeof h);
@@ -359,6 +369,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         h.tbl_hs_lam = rp && c->rp_lam.p ? c->rp_lam.p + (size_t)it * M : nullptr;
         h.tbl_hs_nu_next = next_in && c->rp_nu.p ? c->rp_nu.p + (size_t)(it + 1) * M : nullptr;
         launch_hyper(h, c->stream);
+        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 3], c->stream));
         launches += 2 + hyper_launch_count(c->kind);
 
         if (emit_all || (it >= c->burn_in && it % c->thinning == 0))                     // :257-259
@@ -379,6 +390,12 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     }
     float ms = 0; BRR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_ms = ms; c->last_launches = launches;
+    c->last_kernel_ms[0] = c->last_kernel_ms[1] = c->last_kernel_ms[2] = 0;
+    for (int n = 0; n < n_iter; ++n)
+        for (int k = 0; k < 3; ++k) {
+            float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, c->kev[4 * n + k], c->kev[4 * n + k + 1]));
+            c->last_kernel_ms[k] += t;
+        }
 }
 
 void check_iters(int max_iterations, int burn_in, int thinning)
@@ -527,6 +544,33 @@ extern "C" int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *la
         BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
         if (ms) *ms = c->last_ms;
         if (launches) *launches = c->last_launches;
+    });
+}
+extern "C" int brr_chain_kernel_ms(const brr_chain *c, double *gram_sweep_hyper_ms)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && gram_sweep_hyper_ms, BRR_E_ARG, "null pointer");
+        for (int k = 0; k < 3; ++k) gram_sweep_hyper_ms[k] = c->last_kernel_ms[k];
+    });
+}
+extern "C" int brr_chain_sweep_profile(const brr_chain *c, double *out8)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && out8 && c->initialised, BRR_E_ARG, "bad arguments");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        long long h[8];
+        BRR_CUDA(cudaMemcpy(h, c->prof.p, sizeof h, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
+    });
+}
+extern "C" int brr_chain_geometry(const brr_chain *c, int *block, int *workers, int *rows_per_worker_max, int *smem_bytes)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
+        if (block) *block = c->B;
+        if (workers) *workers = c->nW;
+        if (rows_per_worker_max) *rows_per_worker_max = c->seg_bytes * 4;
+        if (smem_bytes) *smem_bytes = (int)c->smem;
     });
 }
 extern "C" void brr_chain_destroy(brr_chain *c)

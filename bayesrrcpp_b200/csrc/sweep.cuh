@@ -56,6 +56,7 @@ struct SweepParams {
     const double *tbl_fix_z;      // F or null
     // grid protocol
     unsigned *arrive, *go;        // zeroed before launch
+    long long *prof;              // optional cycle accounting of the sampler CTA: wait, reduce, pass, publish, windows, full steps, blocks
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
     double *partials;             // nW x PS
     double *bcast;                // 3 x PS: delta, a*delta, d*delta (visiting order within the block)

@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench.py -- SNP-updates/s of the per-SNP Gibbs sweep (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one Gibbs iteration: one pass of the hot path (block Gram -> persistent sweep -> hyper draws) over all M
+markers.  N=1 workload = BASELINE.json configs[1]: BayesRSamplerV2, N=50,000 x M=50,000 synthetic genotypes, simulated
+phenotype h2=0.5, K=4.  Rank r of a multi-GPU run holds its own N-row shard (weak scaling, see DESIGN.md "Multi-GPU").
+
+  value     : whole-job SNP-updates/s, genotypes resident in HBM, device-timed (CUDA events on the chain's stream)
+  e2e       : same metric through the C ABI with HOST buffers: packed genotypes H2D, chain creation, per-iteration
+              permutation upload, sample rows D2H + CSV writer (thinning 10) all inside the timed region (wall clock)
+  roofline  : the persistent sweep kernel against the measured HBM copy bandwidth (it is bound by the serial chain,
+              not by HBM -- DESIGN.md section 4)
+  cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's Eigen sampler; R, Rcpp and Eigen are
+              absent, the reference itself cannot be built) on a bounded column sample of the same workload, 1 core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=50000, M=50000, cva=[1e-4, 1e-3, 1e-2], h2=0.5, causal_frac=0.1,
+           hyp=dict(sigma0=0.01, v0E=1e-4, s02E=1e-3, v0G=1e-4, s02G=1e-3), data_seed=1002, chain_seed=2002,
+           chain_burn=20)
+WORKLOAD = "BayesRSamplerV2 N=50000 x M=50000 K=4 synthetic 2-bit genotypes, simulated phenotype h2=0.5 (BASELINE configs[1])"
+CPU_SAMPLE_M = 4000          # columns of the dense fp64 sample the CPU arm sweeps (full N)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def simulate_phenotype(geno, seed, h2, causal_frac):
+    rng = np.random.default_rng(seed)
+    M, N = geno.M, geno.N
+    mc = max(1, int(round(causal_frac * M)))
+    b = np.zeros(M)
+    b[rng.choice(M, mc, replace=False)] = rng.normal(0, np.sqrt(h2 / mc), size=mc)
+    y = geno.matvec(b) + rng.normal(0, np.sqrt(1 - h2), size=N)
+    return (y - y.mean()) / y.std(ddof=1)
+
+
+def cpu_sample_data(N, M_s, seed):
+    """dense fp64 column sample of the workload for the CPU arm (numpy only: runs without a GPU)"""
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0.05, 0.5, size=M_s)
+    X = np.empty((N, M_s), order="F")
+    for j in range(M_s):
+        g = rng.binomial(2, p[j], size=N).astype(np.float64)
+        sd = g.std(ddof=1)
+        X[:, j] = (g - g.mean()) / (sd if sd > 0 else 1.0)
+    b = np.zeros(M_s)
+    idx = rng.choice(M_s, max(1, M_s // 10), replace=False)
+    b[idx] = rng.normal(0, np.sqrt(0.5 / len(idx)), size=len(idx))
+    y = X @ b + rng.normal(0, np.sqrt(0.5), size=N)
+    return X, (y - y.mean()) / y.std(ddof=1)
+
+
+def run_cpu_arm(steps, warmup):
+    """the reference's CPU algorithm (oracle port), single thread like the reference's sampler thread"""
+    from oracle import pyoracle as po
+    po.build()
+    X, y = cpu_sample_data(CFG["N"], CPU_SAMPLE_M, CFG["data_seed"])
+    kw = dict(CFG["hyp"])
+    po.run_v2(X, y, CFG["cva"], max(1, warmup), seed=1, want_rows=False, **kw)          # warm-up (page-in, caches)
+    r = po.run_v2(X, y, CFG["cva"], steps, seed=CFG["chain_seed"], want_rows=False, **kw)
+    rate = CPU_SAMPLE_M * steps / r["seconds"]
+    sample = "full N=%d rows x %d-column dense fp64 sample, %d iterations, oracle -O2 (per-marker cost is independent of M: extrapolates)" % (
+        CFG["N"], CPU_SAMPLE_M, steps)
+    return rate, r["seconds"], sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--burn", type=int, default=CFG["chain_burn"], help="untimed chain burn-in iterations before the warm-up")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 20))
+        rate, secs, sample = run_cpu_arm(steps, 1)
+        print(json.dumps({"impl": "reference", "metric": "SNP-updates/sec", "value": rate, "unit": "SNP-updates/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * secs / steps * CFG["M"] / CPU_SAMPLE_M,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": WORKLOAD, "sample": sample},
+                          "cpu_baseline": {"value": rate, "unit": "SNP-updates/s", "cores": 1, "kind": "port", "sample": sample},
+                          "e2e": {"value": rate, "unit": "SNP-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import bayesrrcpp_b200 as brr
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local
+    N, M = CFG["N"], CFG["M"]
+    geno = brr.Genotypes.synthetic(N, M, CFG["data_seed"] + 7919 * rank, device=dev)
+    y = simulate_phenotype(geno, CFG["data_seed"] + rank, CFG["h2"], CFG["causal_frac"])
+    total_iters = args.burn + W + args.steps
+    chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"] + rank, Y=y, cva=CFG["cva"], block=args.block, **CFG["hyp"])
+    chain.run_discard(args.burn)           # untimed chain burn-in: the timed steps see a settled sparsity pattern
+    chain.run_discard(W)                           # warm-up steps
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    barrier()
+    with ClockSampler(dev) as clk:
+        chain.run_discard(args.steps)              # timed: device time between CUDA events on the chain's stream
+        barrier()
+    ms, launches = chain.last_timing()
+    kms = chain.kernel_ms()
+    prof = chain.sweep_profile()
+    geom = chain.geometry()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * M * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers (every rank; max time over ranks)
+    e2e = None
+    if not args.no_e2e:
+        codes = geno.codes()                                           # host packed genotypes (outside the timed region)
+        st = geno.stats()
+        thin = 10
+        tmp = tempfile.NamedTemporaryFile(suffix=".csv", delete=False); tmp.close()
+        barrier()
+        t0 = time.perf_counter()
+        g2 = brr.Genotypes.from_packed(codes, N, mean=st["mean"], sd=st["sd"], device=dev)    # H2D of the packed matrix
+        c2 = brr.Chain(g2, brr.V2, args.steps, burn_in=1, thinning=thin, seed=CFG["chain_seed"] + rank, Y=y, cva=CFG["cva"],
+                       block=args.block, **CFG["hyp"])
+        c2.open_output(tmp.name)
+        kept = c2.run_discard(args.steps)                              # perm H2D per step, kept rows D2H + CSV writer
+        c2.close_output()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        row_bytes = 8 * (2 * M + 4 + N)
+        e2e = {"value": world * M * args.steps / dt, "unit": "SNP-updates/s",
+               "h2d_bytes_per_step": int(codes.nbytes / args.steps + 4 * M + 8 * N / args.steps),
+               "d2h_bytes_per_step": int(row_bytes * kept / args.steps),
+               "note": "brr_geno_from_packed(host codes) + brr_chain_create + %d iterations with CSV rows every %d; wall clock" % (args.steps, thin)}
+        c2.close(); g2.close()
+        os.unlink(tmp.name)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    algo_bytes = M * ((N + 3) // 4) + 16 * N + 24 * M                  # per sweep launch
+    sweep_ms = kms["sweep"] / args.steps
+    achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
+    out = {"metric": "SNP-updates/sec", "value": value, "unit": "SNP-updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+           "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "block": geom["block"], "workers": geom["workers"],
+                      "rows_per_worker_max": geom["rows_per_worker_max"], "chain_burn_in_iterations": args.burn,
+                      "l2": "inputs larger than L2: 625 MB of packed genotypes are re-read every step",
+                      "parallelism": "1 GPU" if world == 1 else "%d independent row shards (replicas; no exchange yet)" % world,
+                      "gibbs_iterations_per_s": world * 1e3 * args.steps / ms_max if world == 1 else 1e3 * args.steps / ms_max},
+           "gpu_launches": int(launches),
+           "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
+           "sampler_cta_cycles_per_block": {k: prof[k] / max(prof["blocks"], 1) for k in ("wait", "reduce", "serial_pass", "publish")},
+           "markers_per_speculative_window": (M * args.steps) / max(prof["windows"], 1),
+           "state_changing_marker_fraction": prof["full_steps"] / (M * args.steps),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "kernel": "sweep_kernel", "peak_source": peak_src,
+                        "note": "serial Gibbs chain: the kernel is latency-bound (M dependent marker steps), see DESIGN.md 4"},
+           "clocks": clk.summary()}
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu and world == 1:
+        rate, secs, sample = run_cpu_arm(10, 1)
+        out["cpu_baseline"] = {"value": rate, "unit": "SNP-updates/s", "cores": 1, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -256,3 +256,75 @@ def synth(N, M, seed, h2=0.5, causal_frac=0.1):
     y = g + rng.normal(0, np.sqrt(max(1e-12, 1 - h2)), size=N)
     y = (y - y.mean()) / y.std(ddof=1)
     return dict(G=G, X=X, y=y, b=b, mean=mean, sd=sd)
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's OWN sources compiled against oracle/shim (only where /root/reference exists)
+REF_LIB = os.path.join(_DIR, "_ref", "libbayesrr_ref.so")
+
+
+def ref_available():
+    if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference/src"):
+        try:
+            build("ref")
+        except Exception:
+            return False
+    return os.path.exists(REF_LIB)
+
+
+def _ref():
+    if "ref" not in _LIBS:
+        lib()                                          # liboracle.so first: _ref links against it
+        L = C.CDLL(REF_LIB)
+        for f in ("ref_v2", "ref_groups", "ref_grstart", "ref_horseshoe"):
+            getattr(L, f).restype = C.c_long
+        _LIBS["ref"] = L
+    return _LIBS["ref"]
+
+
+def ref_v2(out, seed, max_it, burn_in, thinning, X, Y, cva, sigma0=0.01, v0E=1e-4, s02E=1e-3, v0G=1e-4, s02G=1e-3):
+    X = _f64(X, "F"); Y = _f64(Y); cva = _f64(cva); N, M = X.shape
+    nr = _n_rows(max_it, burn_in, thinning, False)
+    rows = np.zeros((nr, 2 * M + 4 + N))
+    n = _ref().ref_v2(os.fsencode(out), C.c_uint64(seed), max_it, burn_in, thinning, _p(X), C.c_long(N), C.c_long(M), _p(Y),
+                      C.c_double(sigma0), C.c_double(v0E), C.c_double(s02E), C.c_double(v0G), C.c_double(s02G), _p(cva),
+                      len(cva), _p(rows), C.c_long(nr))
+    return rows, n
+
+
+def ref_groups(out, seed, max_it, burn_in, thinning, X, Y, cva, groups, gAssign, fixed, sigma0=0.01, v0E=1e-4, s02E=1e-3,
+               v0G=1e-4, s02G=1e-3):
+    X = _f64(X, "F"); Y = _f64(Y); cva = _f64(np.atleast_2d(cva), "F"); N, M = X.shape
+    fixed = _f64(fixed, "F") if fixed is not None else np.zeros((N, 0), order="F")
+    F = fixed.shape[1]
+    gA = np.ascontiguousarray(gAssign, dtype=np.int32)
+    nr = _n_rows(max_it, burn_in, thinning, False)
+    rows = np.zeros((nr, 2 * M + 3 + groups + N + F + 1))
+    n = _ref().ref_groups(os.fsencode(out), C.c_uint64(seed), max_it, burn_in, thinning, _p(X), C.c_long(N), C.c_long(M), _p(Y),
+                          C.c_double(sigma0), C.c_double(v0E), C.c_double(s02E), C.c_double(v0G), C.c_double(s02G), _p(cva),
+                          cva.shape[1], groups, gA.ctypes.data_as(_ip), _p(fixed) if F else _dp(), C.c_long(F), _p(rows), C.c_long(nr))
+    return rows, n
+
+
+def ref_grstart(out, seed, max_it, burn_in, thinning, mu, beta, sigmaE, sigmaGG, X, epsilon, components, cva, groups, gAssign,
+                sigma0=0.01, v0E=1e-4, s02E=1e-3, v0G=1e-4, s02G=1e-3):
+    X = _f64(X, "F"); cva = _f64(np.atleast_2d(cva), "F"); N, M = X.shape
+    beta = _f64(beta).ravel(); eps = _f64(epsilon); comp = _f64(components); sg = _f64(sigmaGG)
+    gA = np.ascontiguousarray(gAssign, dtype=np.int32)
+    nr = _n_rows(max_it, burn_in, thinning, False)
+    rows = np.zeros((nr, 2 * M + 3 + groups + N))
+    n = _ref().ref_grstart(os.fsencode(out), C.c_uint64(seed), max_it, burn_in, thinning, C.c_double(mu), _p(beta), C.c_double(sigmaE),
+                           _p(sg), _p(X), C.c_long(N), C.c_long(M), _p(eps), _p(comp), C.c_double(sigma0), C.c_double(v0E),
+                           C.c_double(s02E), C.c_double(v0G), C.c_double(s02G), _p(cva), cva.shape[1], groups,
+                           gA.ctypes.data_as(_ip), _p(rows), C.c_long(nr))
+    return rows, n
+
+
+def ref_horseshoe(out, seed, max_it, burn_in, thinning, X, Y, A, v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0):
+    X = _f64(X, "F"); Y = _f64(Y); N, M = X.shape
+    nr = _n_rows(max_it, burn_in, thinning, False)
+    rows = np.zeros((nr, 2 * M + 4 + N))
+    n = _ref().ref_horseshoe(os.fsencode(out), C.c_uint64(seed), max_it, burn_in, thinning, _p(X), C.c_long(N), C.c_long(M), _p(Y),
+                             C.c_double(A), C.c_double(v0E), C.c_double(s02E), C.c_double(vL), C.c_double(vT), C.c_double(c2),
+                             C.c_double(vC), C.c_double(sC), _p(rows), C.c_long(nr))
+    return rows, n

@@ -384,3 +384,66 @@ def test_entry_points_groups_restart_horseshoe_files(po, brr, tmp_path):
     assert lines[0] + "\n" == po.format_header(po.KIND_HORSESHOE, N, M) and lines[0].endswith(",")
     rows3 = [np.array([float(x) for x in ln.split(", ")]) for ln in lines[1:-1]]
     assert len(rows3) == o3["n_rows"] == 2 and all(np.allclose(r, o3["rows"][i], rtol=2e-5, atol=1e-12) for i, r in enumerate(rows3))
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors of the reference's own sources
+def _gold(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"), allow_pickle=False)
+    return z, np.asfortranarray((z["G"] - z["mean"]) / z["sd"])
+
+
+def test_gpu_replays_reference_golden_v2(po, brr):
+    """tests/golden/v2.npz holds rows packed by the reference's own BayesRv2.cpp; the draws it consumed are re-derived by
+    running the oracle on the same sequential stream with recording on, then replayed on the GPU."""
+    z, X = _gold("v2")
+    N, M = X.shape
+    T, burn, thin = int(z["max_iterations"]), int(z["burn_in"]), int(z["thinning"])
+    t = po.DrawTables(T, M, n_gam=6, n_init_u=1)
+    pi0 = [0.5, np.nan, np.nan, np.nan]
+    po.run_v2(X, z["y"], z["cva"], T, source=po.SRC_SEQ, seed=int(z["seed"]), tables=t, record=True, pi_init=pi0, **HYP)
+    g = brr.Genotypes.from_dense(X)
+    c = brr.Chain(g, brr.V2, T, burn_in=burn, thinning=thin, Y=z["y"], cva=z["cva"], pi_init=pi0, **HYP)
+    c.set_replay(t)
+    rows = c.run(T, emit_all=False)
+    a, b = V2Row(rows, N, M), V2Row(z["rows"], N, M)
+    assert rows.shape == z["rows"].shape and np.array_equal(a.comp, b.comp)
+    assert_trace_close("beta", a.beta, b.beta, TOL); assert_trace_close("epsilon", a.eps, b.eps, TOL)
+    assert rel_inf(a.sigmaG, b.sigmaG) <= TOL and rel_inf(a.sigmaE, b.sigmaE) <= TOL and rel_inf(a.mu, b.mu) <= TOL
+
+
+def test_gpu_replays_reference_golden_groups_and_restart(po, brr):
+    z, X = _gold("groups")
+    N, M = X.shape; G, F, K = 3, 2, 4
+    T, burn, thin = int(z["max_iterations"]), int(z["burn_in"]), int(z["thinning"])
+    t = po.DrawTables(T, M, n_gam=2 + G * (K + 1), F=F, n_init_u=G + 1)
+    po.run_groups(X, z["y"], z["cva"], G, z["gAssign"], z["fixed"], T, source=po.SRC_SEQ, seed=int(z["seed"]), tables=t, record=True, **HYP)
+    g = brr.Genotypes.from_dense(X)
+    c = brr.Chain(g, brr.GROUPS, T, burn_in=burn, thinning=thin, Y=z["y"], cva=z["cva"], groups=G, gAssign=z["gAssign"], fixed=z["fixed"], **HYP)
+    c.set_replay(t)
+    _compare_groups(dict(rows=z["rows"]), c.run(T, emit_all=False), N, M, G, F)
+    z, X = _gold("grstart")
+    T, burn, thin = int(z["max_iterations"]), int(z["burn_in"]), int(z["thinning"])
+    t = po.DrawTables(T, M, n_gam=2 + G * (K + 1), n_init_g=G * (K + 1))
+    st = dict(mu=float(z["mu"]), beta=z["beta"], sigmaE=float(z["sigmaE"]), sigmaGG=z["sigmaGG"], epsilon=z["epsilon"], components=z["components"])
+    po.run_grstart(st["mu"], st["beta"], st["sigmaE"], st["sigmaGG"], X, st["epsilon"], st["components"], z["cva"], G, z["gAssign"], T,
+                   source=po.SRC_SEQ, seed=int(z["seed"]), tables=t, record=True, **HYP)
+    c = brr.Chain(g, brr.GRSTART, T, burn_in=burn, thinning=thin, cva=z["cva"], groups=G, gAssign=z["gAssign"], **st, **HYP)
+    c.set_replay(t)
+    _compare_groups(dict(rows=z["rows"]), c.run(T, emit_all=False), N, M, G, 0, restart=True)
+
+
+def test_gpu_replays_reference_golden_horseshoe(po, brr):
+    z, X = _gold("horseshoe")
+    N, M = X.shape
+    T, burn, thin = int(z["max_iterations"]), int(z["burn_in"]), int(z["thinning"])
+    t = po.DrawTables(T, M, n_gam=4, n_init_u=1, n_init_g=2 * M + 2, horseshoe=True)
+    po.run_horseshoe(X, z["y"], float(z["A"]), T, source=po.SRC_SEQ, seed=int(z["seed"]), tables=t, record=True)
+    g = brr.Genotypes.from_dense(X)
+    c = brr.Chain(g, brr.HORSESHOE, T, burn_in=burn, thinning=thin, Y=z["y"], A=float(z["A"]), v0E=1e-3, s02E=1e-3)
+    c.set_replay(t)
+    rows = c.run(T, emit_all=False)
+    a, b = HsRow(rows, N, M), HsRow(z["rows"], N, M)
+    for name in ("beta", "eps", "lam"):
+        assert_trace_close(name, getattr(a, name), getattr(b, name), TOL)
+    assert rel_inf(a.tau, b.tau) <= TOL and rel_inf(a.sigmaE, b.sigmaE) <= TOL and rel_inf(a.mu, b.mu) <= TOL
