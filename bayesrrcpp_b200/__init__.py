@@ -268,9 +268,10 @@ class Chain:
         return dict(gram=out[0], sweep=out[1], hyper=out[2])
 
     def sweep_profile(self):
-        o = np.zeros(8)
+        o = np.zeros(16)
         _check(lib().brr_chain_sweep_profile(self._h, _p(o)))
-        return dict(wait=o[0], reduce=o[1], serial_pass=o[2], publish=o[3], windows=o[4], full_steps=o[5], blocks=o[6])
+        return dict(gather=o[0], window_cycles=o[1], serial_pass=o[2], publish=o[3], windows=o[4], full_steps=o[5], blocks=o[6],
+                    full_cycles=o[7], worker_wait=o[8], worker_apply=o[9], worker_dots=o[10])
 
     def geometry(self):
         b, w, r, s = C.c_int(), C.c_int(), C.c_int(), C.c_int()

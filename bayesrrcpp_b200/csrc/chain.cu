@@ -58,10 +58,10 @@ struct brr_chain {
     int B = 128, TW = 1, nW = 1, seg_bytes = 16, PS = 128, nb = 0; size_t smem = 0;
     // device state
     DevBuf<double> eps, beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
-    DevBuf<double> partials, bcast, fin;
+    DevBuf<double> fin;
+    DevBuf<uint64_t> ll;                     // flagged-word hand-over buffers: [nW*PS*2 | (3*PS+1)*2]
     DevBuf<int32_t> d_gAssign, unit0, gram;
     DevBuf<IterScalars> sc;
-    DevBuf<unsigned> sync;
     DevBuf<int> abort_flag;
     DevBuf<long long> prof;
     PinBuf<int32_t> h_perm[PERM_RING]; DevBuf<int32_t> d_perm[PERM_RING]; cudaEvent_t perm_free[PERM_RING] = {}; bool perm_used[PERM_RING] = {};
@@ -121,7 +121,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     int dev = 0, sms = 0;
     BRR_CUDA(cudaGetDevice(&dev));
     BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int kidx = c->kind == BRR_HORSESHOE ? 1 : 0;
+    const int kidx = c->kind == BRR_HORSESHOE ? 1 : (c->K == 3 || c->K == 4) ? 2 : 0;   // sweep-kernel variant
     BRR_REQUIRE(c->kind == BRR_HORSESHOE || (c->K >= 2 && c->K <= KMAX), BRR_E_SIZE,
                 "number of mixture components must be in [2, " + std::to_string(KMAX) + "]");
     const int64_t units = (c->N + 63) / 64;
@@ -136,7 +136,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         BRR_REQUIRE(TW != 0, BRR_E_SIZE, "more than 2048 rows per worker CTA (" + std::to_string(maxu * 64) +
                     "): shard the individuals over more devices");
         const int seg = (int)maxu * 16;
-        const size_t smem = sweep_smem_bytes(kidx, B, c->K, c->G, (int)c->F, seg);
+        const size_t smem = sweep_smem_bytes(kidx, B, TW, c->K, c->G, (int)c->F, seg);
         if (smem > 227 * 1024) {
             BRR_REQUIRE(B > 32, BRR_E_SIZE, "sweep kernel does not fit shared memory (reduce K or groups)");
             B /= 2; continue;
@@ -237,12 +237,10 @@ void chain_init(brr_chain *c)
         c->fixG.from(fg); c->alpha.from(al);
     }
     std::vector<IterScalars> scv(1, sc); c->sc.from(scv);
-    c->partials.alloc((size_t)c->nW * c->PS); c->partials.zero();
-    c->bcast.alloc((size_t)3 * c->PS); c->bcast.zero();
+    c->ll.alloc(((size_t)c->nW * c->PS + 4 * (size_t)c->PS + 1) * 2); c->ll.zero();
     c->fin.alloc((size_t)2 * c->nW); c->fin.zero();
-    c->sync.alloc(2);
     c->abort_flag.alloc(1); c->abort_flag.zero();
-    c->prof.alloc(8); c->prof.zero();
+    c->prof.alloc(16); c->prof.zero();
     c->gram.alloc((size_t)c->nb * c->B * c->B);
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
@@ -308,7 +306,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     BRR_CUDA(cudaSetDevice(c->g->device));
     if (!c->initialised) chain_init(c);
     const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
-    const int kk = c->kind == BRR_HORSESHOE ? 1 : 0;
+    const int kk = c->kind == BRR_HORSESHOE ? 1 : (K == 3 || K == 4) ? 2 : 0;   // sweep-kernel variant
     int64_t launches = 0;
     c->prof.zero(c->stream);
     while (c->kev.size() < (size_t)4 * n_iter) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
@@ -333,7 +331,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
 
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
         launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
-        BRR_CUDA(cudaMemsetAsync(c->sync.p, 0, 2 * sizeof(unsigned), c->stream));
+        c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 
         SweepParams p; memset(&p, 0, sizeof p);
@@ -349,7 +347,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
         p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
-        p.arrive = c->sync.p; p.go = c->sync.p + 1; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.partials = c->partials.p; p.bcast = c->bcast.p; p.fin = c->fin.p;
+        p.ll_part = c->ll.p; p.ll_red = c->ll.p + (size_t)c->nW * c->PS * 2; p.ll_bcast = p.ll_red + (size_t)c->PS * 2; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
         p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
@@ -553,14 +551,14 @@ extern "C" int brr_chain_kernel_ms(const brr_chain *c, double *gram_sweep_hyper_
         for (int k = 0; k < 3; ++k) gram_sweep_hyper_ms[k] = c->last_kernel_ms[k];
     });
 }
-extern "C" int brr_chain_sweep_profile(const brr_chain *c, double *out8)
+extern "C" int brr_chain_sweep_profile(const brr_chain *c, double *out16)
 {
     return guarded([&] {
-        BRR_REQUIRE(c && out8 && c->initialised, BRR_E_ARG, "bad arguments");
+        BRR_REQUIRE(c && out16 && c->initialised, BRR_E_ARG, "bad arguments");
         BRR_CUDA(cudaSetDevice(c->g->device));
-        long long h[8];
+        long long h[16];
         BRR_CUDA(cudaMemcpy(h, c->prof.p, sizeof h, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
+        for (int i = 0; i < 16; ++i) out16[i] = (double)h[i];
     });
 }
 extern "C" int brr_chain_geometry(const brr_chain *c, int *block, int *workers, int *rows_per_worker_max, int *smem_bytes)

@@ -55,11 +55,11 @@ struct SweepParams {
     double *alpha;                // F
     const double *tbl_fix_z;      // F or null
     // grid protocol
-    unsigned *arrive, *go;        // zeroed before launch
+    uint64_t *ll_part;            // PS x nW flagged-word slots (2 x u64 each), column-major: workers' partial dots; zeroed before launch
+    uint64_t *ll_red;             // PS slots: column totals, reducer warps -> sampler; zeroed before launch
+    uint64_t *ll_bcast;           // (3 x PS + 1) slots: sampler -> workers delta, a*delta, d*delta (+ sentinel); zeroed before launch
     long long *prof;              // optional cycle accounting of the sampler CTA: wait, reduce, pass, publish, windows, full steps, blocks
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
-    double *partials;             // nW x PS
-    double *bcast;                // 3 x PS: delta, a*delta, d*delta (visiting order within the block)
     double *fin;                  // nW x 2: sum eps, sum eps^2 over the worker's rows
     int nW; int PS;
     const int32_t *unit0;         // nW + 1: first 64-row unit of every worker
@@ -70,7 +70,7 @@ struct SweepParams {
 struct SweepGeom { int B, TW, nW, seg_bytes; size_t smem_bytes; };
 
 void launch_sweep(int kind, int B, int TW, const SweepParams &p, size_t smem, cudaStream_t stream);
-size_t sweep_smem_bytes(int kind, int B, int K, int G, int F, int seg_bytes);
+size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, cudaStream_t stream);

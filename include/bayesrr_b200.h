@@ -151,10 +151,11 @@ int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches);
 /* device time (ms, CUDA events on the chain's stream) of the last brr_chain_run split by kernel: [0] block-Gram kernel,
  * [1] persistent sweep kernel, [2] hyper-parameter kernel(s); summed over the iterations of that run */
 int brr_chain_kernel_ms(const brr_chain *c, double *gram_sweep_hyper_ms);
-/* SM-clock cycle accounting of the sampler CTA over the last brr_chain_run: [0] waiting for the workers' partial dots,
- * [1] fixed-order reduction, [2] the serial in-block pass, [3] publishing the deltas, [4] speculative windows,
- * [5] full per-marker steps, [6] blocks */
-int brr_chain_sweep_profile(const brr_chain *c, double *out8);
+/* SM-clock cycle accounting over the last brr_chain_run (16 values).  Sampler CTA: [0] gathering the workers' partial
+ * dots, [1] speculative windows, [2] the whole serial in-block pass, [3] publishing the deltas, [4] number of windows,
+ * [5] number of state-changing marker steps, [6] blocks, [7] cycles in state-changing steps.  First worker CTA:
+ * [8] waiting for the deltas, [9] residual update, [10] dot stage + send */
+int brr_chain_sweep_profile(const brr_chain *c, double *out16);
 /* launch geometry chosen for the sweep kernel */
 int brr_chain_geometry(const brr_chain *c, int *block, int *workers, int *rows_per_worker_max, int *smem_bytes);
 /* flush the writer and close the output file */
