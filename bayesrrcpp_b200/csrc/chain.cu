@@ -347,7 +347,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
         p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
-        p.ll_part = c->ll.p; p.ll_red = c->ll.p + (size_t)c->nW * c->PS * 2; p.ll_bcast = p.ll_red + (size_t)c->PS * 2; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
+        p.ll_part = c->ll.p; p.ll_red = c->ll.p + (size_t)c->nW * c->PS * 2; p.ll_bcast = p.ll_red + (size_t)c->PS * 2; p.ll_delta = p.ll_bcast + (size_t)c->PS * 2; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
         p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));

@@ -57,6 +57,7 @@ struct SweepParams {
     // grid protocol
     uint64_t *ll_part;            // PS x nW flagged-word slots (2 x u64 each), column-major: workers' partial dots; zeroed before launch
     uint64_t *ll_red;             // PS slots: column totals, reducer warps -> sampler; zeroed before launch
+    uint64_t *ll_delta;           // PS slots: the sampler's per-marker deltas of the current block, streamed as they are decided
     uint64_t *ll_bcast;           // (3 x PS + 1) slots: sampler -> workers delta, a*delta, d*delta (+ sentinel); zeroed before launch
     long long *prof;              // optional cycle accounting of the sampler CTA: wait, reduce, pass, publish, windows, full steps, blocks
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
