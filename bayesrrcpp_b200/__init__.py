@@ -115,6 +115,11 @@ class Genotypes:
         _check(lib().brr_geno_synthetic(C.c_int64(N), C.c_int64(M), C.c_uint64(seed), C.c_int64(row0), C.c_int(device), C.byref(h)))
         return cls(h)
 
+    def shard_stats(self, comm):
+        """make the per-SNP statistics those of the whole matrix (collective over `comm`, a sharded.Comm)"""
+        _check(lib().brr_geno_shard_stats(self._h, comm.byref()))
+        return self
+
     def stats(self):
         out = {k: np.zeros(self.M) for k in ("mean", "sd", "a", "d", "xsq")}
         _check(lib().brr_geno_stats(self._h, _p(out["mean"]), _p(out["sd"]), _p(out["a"]), _p(out["d"]), _p(out["xsq"])))
@@ -171,8 +176,9 @@ class Chain:
     def __init__(self, geno, kind, max_iterations, burn_in=1, thinning=1, seed=1, Y=None,
                  sigma0=0.01, v0E=1e-4, s02E=1e-3, v0G=1e-4, s02G=1e-3, cva=None, groups=1, gAssign=None, fixed=None,
                  pi_init=None, mu=0.0, beta=None, sigmaE=0.0, sigmaGG=None, epsilon=None, components=None,
-                 A=0.0, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=0, gram_impl=0, workers=0):
-        self.geno, self.kind = geno, kind
+                 A=0.0, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=0, gram_impl=0, workers=0, comm=None):
+        """comm: a sharded.Comm -> row-sharded chain (Y / fixed / epsilon hold this rank's rows; collective call)"""
+        self.geno, self.kind, self.comm = geno, kind, comm
         keep = []
 
         def arr(a, fortran=False):
@@ -209,7 +215,10 @@ class Chain:
         self.G = groups if kind in (GROUPS, GRSTART) else 1
         self.F = cfg.F
         h = C.c_void_p()
-        _check(lib().brr_chain_create(C.byref(cfg), geno._h, C.byref(h)))
+        if comm is None:
+            _check(lib().brr_chain_create(C.byref(cfg), geno._h, C.byref(h)))
+        else:
+            _check(lib().brr_chain_create_sharded(C.byref(cfg), geno._h, comm.byref(), C.byref(h)))
         self._h = h
         self._keep = keep
         self.row_len = lib().brr_chain_row_len(self._h)

@@ -5,6 +5,7 @@
 // the CPU except initial scalars, the O(M) marker shuffle (std::random_shuffle in the reference, :182) and row packing.
 #include "sweep.cuh"
 #include "hyper.cuh"
+#include "shard.cuh"
 #include "writer.h"
 #include <algorithm>
 #include <cmath>
@@ -45,7 +46,12 @@ struct RowSnap {            // one in-flight sample row
 
 struct brr_chain {
     brr_geno *g = nullptr;
-    int kind = 0, K = 0, G = 1; int64_t N = 0, M = 0, F = 0;
+    int kind = 0, K = 0, G = 1; int64_t N = 0, M = 0, F = 0;     // N: rows of this rank
+    int64_t N_total = 0;                                          // rows of all ranks (== N unless row-sharded)
+    brr_comm comm{0, 1, nullptr, nullptr, nullptr};
+    Window win;                                                   // exchange window (holds eps; peers write / read it when sharded)
+    double *d_eps = nullptr;                                      // = win.eps(rank)
+    DevBuf<int32_t> gram_part_unused;
     uint64_t seed = 0; PhiloxKey key{0, 0};
     int max_iterations = 0, burn_in = 0, thinning = 1;
     double sigma0 = 0, v0E = 0, s02E = 0, v0G = 0, s02G = 0;
@@ -57,9 +63,9 @@ struct brr_chain {
     // geometry
     int B = 128, TW = 1, nW = 1, seg_bytes = 16, PS = 128, nb = 0; size_t smem = 0;
     // device state
-    DevBuf<double> eps, beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
+    DevBuf<double> beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
     DevBuf<double> fin;
-    DevBuf<uint64_t> ll;                     // flagged-word hand-over buffers: [nW*PS*2 | (3*PS+1)*2]
+    DevBuf<uint64_t> ll;                     // flagged-word hand-over buffers inside the device: [part nW*PS | bcast PS | delta 2*PS+1 | fin 2*nW] slots
     DevBuf<int32_t> d_gAssign, unit0, gram;
     DevBuf<IterScalars> sc;
     DevBuf<int> abort_flag;
@@ -81,6 +87,7 @@ struct brr_chain {
 
     int64_t row_len() const
     {
+        const int64_t N = N_total;
         switch (kind) {
         case BRR_V2: return 2 * M + 4 + N;                   // reference src/BayesRv2.cpp:136
         case BRR_GROUPS: return 2 * M + 3 + G + N + F + 1;   // src/BayesRv2Groups.cpp:152
@@ -97,6 +104,7 @@ struct brr_chain {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
+        win.release();
     }
 };
 
@@ -162,17 +170,21 @@ void chain_init(brr_chain *c)
     IterScalars sc; memset(&sc, 0, sizeof sc);
     std::vector<double> eps(c->g->Npad, 0.0), beta(M, 0.0), comp(M, 0.0), sigG(G, 0.0), pi((size_t)G * std::max(K, 1), 0.0);
     double mu = 0.0;
+    const double n_all = (double)c->N_total;
+    // ||v||^2 and sum(v) over the rows of ALL ranks (row-sharded chains: host allreduce at set-up time)
+    auto all_sqnorm = [&](const double *x) { double v = host_sqnorm(x, N); comm_allreduce(c->comm, &v, 1); return v; };
+    auto all_sum = [&](const double *x) { double v = host_sum(x, N); comm_allreduce(c->comm, &v, 1); return v; };
     if (c->kind == BRR_V2) {
         sigG[0] = init_uniform(c, 0);                                                   // src/BayesRv2.cpp:162
         for (int k = 0; k < K; ++k) pi[k] = c->pi_init[k];                              // :150,:164 (Q1)
         for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu - 0.0;                    // :168 (beta == 0)
-        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :169
+        sc.sigmaE = all_sqnorm(eps.data()) / n_all * 0.5;                               // :169
     } else if (c->kind == BRR_GROUPS) {
         for (int g = 0; g < G; ++g) { pi[(size_t)g * K] = 0.5; for (int k = 1; k < K; ++k) pi[(size_t)g * K + k] = 0.5 / K; }   // Groups:170-175
         for (int g = 0; g < G; ++g) sigG[g] = init_uniform(c, g);                       // :194-195
         sc.sigmaF = init_uniform(c, G);                                                 // :197
         for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu;                          // :203
-        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :204
+        sc.sigmaE = all_sqnorm(eps.data()) / n_all * 0.5;                               // :204
     } else if (c->kind == BRR_GRSTART) {
         mu = c->mu0; sc.sigmaE = c->sigmaE0;
         beta = c->beta0; comp = c->comp0; sigG = c->sigmaGG0;
@@ -193,7 +205,7 @@ void chain_init(brr_chain *c)
         }
     } else {
         for (int64_t i = 0; i < N; ++i) eps[i] = c->Y[i] - mu - 0.0;                    // HorseshoeR.cpp:186
-        sc.sigmaE = host_sqnorm(eps.data(), N) / N * 0.5;                               // :187
+        sc.sigmaE = all_sqnorm(eps.data()) / n_all * 0.5;                               // :187
         // :171,:176,:179 draw and discard (tau, v, lambda are overwritten at :177,:180,:192); keyed draws need not be consumed
         const double eta0 = 1.0 / ((1.0 / (1 / (sc.sigmaE * std::pow(c->A, 2)))) * init_gamma(c, 2 * M, 0.5));       // :189
         sc.eta = eta0;
@@ -212,14 +224,15 @@ void chain_init(brr_chain *c)
     }
     // first intercept draw (:177-179 of iteration 0)
     {
-        const double es = host_sum(eps.data(), N), n = (double)N;
+        const double es = all_sum(eps.data()), n = n_all;
         const double z = c->replay ? c->rp_mu_h[0] : draw_normal(c->key, S_MU, 0, 0);
         sc.mu = mu;
         sc.mu_next = (es + n * mu) / n + std::sqrt(sc.sigmaE / n) * z;
         sc.shift = mu - sc.mu_next;
         sc.eps_sum = es + n * sc.shift;
     }
-    c->eps.from(eps); c->beta.from(beta); c->comp.from(comp); c->sigmaG.from(sigG); c->pi.from(pi);
+    BRR_CUDA(cudaMemcpy(c->d_eps, eps.data(), eps.size() * 8, cudaMemcpyHostToDevice));
+    c->beta.from(beta); c->comp.from(comp); c->sigmaG.from(sigG); c->pi.from(pi);
     c->vcount.alloc((size_t)G * std::max(K, 1)); c->vcount.zero(); c->betaAcum.alloc(G); c->betaAcum.zero();
     if (c->kind != BRR_HORSESHOE) c->d_cva.from(c->cva);
     if (!c->gAssign.empty()) c->d_gAssign.from(c->gAssign);
@@ -234,11 +247,12 @@ void chain_init(brr_chain *c)
             }
             fg[(size_t)F * F + a] = host_sum(&c->fixed[a * N], N);
         }
+        comm_allreduce(c->comm, fg.data(), (int64_t)fg.size());
         c->fixG.from(fg); c->alpha.from(al);
     }
     std::vector<IterScalars> scv(1, sc); c->sc.from(scv);
-    c->ll.alloc(((size_t)c->nW * c->PS + 4 * (size_t)c->PS + 1) * 2); c->ll.zero();
-    c->fin.alloc((size_t)2 * c->nW); c->fin.zero();
+    c->ll.alloc(((size_t)c->nW * c->PS + 3 * (size_t)c->PS + 1 + 2 * (size_t)c->nW) * 2); c->ll.zero();
+    c->fin.alloc(2); c->fin.zero();
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
     c->gram.alloc((size_t)c->nb * c->B * c->B);
@@ -260,7 +274,7 @@ void chain_init(brr_chain *c)
 void deliver_row(brr_chain *c, RowSnap &s, double *rows, int64_t max_rows, int64_t *n_rows)
 {
     BRR_CUDA(cudaEventSynchronize(s.ready));
-    const int64_t N = c->N, M = c->M, F = c->F; const int G = c->G;
+    const int64_t N = c->N_total, M = c->M, F = c->F; const int G = c->G;
     IterScalars sc; memcpy(&sc, s.scal.p, sizeof sc);
     const double *sg = s.scal.p + sizeof(IterScalars) / 8 + 1;
     double *r = s.row.p;
@@ -284,15 +298,18 @@ void snapshot_row(brr_chain *c, int64_t it, double *rows, int64_t max_rows, int6
 {
     RowSnap &s = c->snaps[c->snap_seq % ROW_RING];
     if (s.pending) { deliver_row(c, s, rows, max_rows, n_rows); ++c->deliver_seq; }
-    const int64_t N = c->N, M = c->M, F = c->F; const int G = c->G;
+    const int64_t N = c->N_total, M = c->M, F = c->F; const int G = c->G;
     double *r = s.row.p; cudaStream_t st = c->stream;
     auto d2h = [&](double *dst, const double *src, int64_t n) { if (n) BRR_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, st)); };
+    // residuals of every rank, straight from the peers' windows: complete once this rank's sweep has ended (it waited for
+    // every rank's end-of-sweep sums) and stable until this rank takes part in the next sweep (stream order)
+    auto eps_all = [&](double *dst) { for (int q = 0; q < c->win.R; ++q) d2h(dst + c->win.row0[q], c->win.eps(q), c->win.n_rows[q]); };
     d2h(r + 2, c->beta.p, M);
     switch (c->kind) {
-    case BRR_V2: d2h(r + 4 + M, c->comp.p, M); d2h(r + 4 + 2 * M, c->eps.p, N); break;
-    case BRR_GROUPS: d2h(r + 3 + M, c->comp.p, M); d2h(r + 3 + 2 * M + G, c->eps.p, N); d2h(r + 3 + 2 * M + G + N, c->alpha.p, F); break;
-    case BRR_GRSTART: d2h(r + 3 + M, c->comp.p, M); d2h(r + 3 + 2 * M + G, c->eps.p, N); break;
-    default: d2h(r + 4 + M, c->lambda.p, M); d2h(r + 4 + 2 * M, c->eps.p, N); break;
+    case BRR_V2: d2h(r + 4 + M, c->comp.p, M); eps_all(r + 4 + 2 * M); break;
+    case BRR_GROUPS: d2h(r + 3 + M, c->comp.p, M); eps_all(r + 3 + 2 * M + G); d2h(r + 3 + 2 * M + G + N, c->alpha.p, F); break;
+    case BRR_GRSTART: d2h(r + 3 + M, c->comp.p, M); eps_all(r + 3 + 2 * M + G); break;
+    default: d2h(r + 4 + M, c->lambda.p, M); eps_all(r + 4 + 2 * M); break;
     }
     BRR_CUDA(cudaMemcpyAsync(s.scal.p, c->sc.p, sizeof(IterScalars), cudaMemcpyDeviceToHost, st));
     d2h(s.scal.p + sizeof(IterScalars) / 8 + 1, c->sigmaG.p, G);
@@ -305,6 +322,8 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
 {
     BRR_CUDA(cudaSetDevice(c->g->device));
     if (!c->initialised) chain_init(c);
+    const bool sharded = c->win.R > 1;
+    if (sharded) { double token = 1.0; comm_allreduce(c->comm, &token, 1); }    // ranks enter the launch sequence together
     const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
     const int kk = c->kind == BRR_HORSESHOE ? 1 : (K == 3 || K == 4) ? 2 : 0;   // sweep-kernel variant
     int64_t launches = 0;
@@ -330,7 +349,11 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         c->perm_used[slot] = true;
 
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
-        launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
+        if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->win.gram(c->win.rank), c->stream);
+            launch_gram_allsum(c->win, (uint32_t)it + 1u, c->gram.p, (size_t)c->nb * c->B * c->B, c->abort_flag.p, c->stream);
+            ++launches;
+        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
         c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 
@@ -339,7 +362,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.packed = g->d_packed; p.stride = g->stride; p.N = g->N;
         p.colA = g->d_a; p.colD = g->d_d; p.colS = g->d_S; p.colXsq = g->d_xsq; p.colCsum = g->d_csum; p.n_total = g->n_total;
         p.perm = c->d_perm[slot].p; p.gram = c->gram.p; p.M = M; p.nb = c->nb; p.it = it;
-        p.eps = c->eps.p; p.beta = c->beta.p; p.comp = c->comp.p; p.sc = c->sc.p;
+        p.eps = c->d_eps; p.beta = c->beta.p; p.comp = c->comp.p; p.sc = c->sc.p;
         p.K = K; p.G = G; p.gAssign = c->d_gAssign.p; p.cva = c->d_cva.p; p.sigmaG = c->sigmaG.p; p.pi = c->pi.p;
         p.vcount = c->vcount.p; p.betaAcum = c->betaAcum.p; p.lambda = c->lambda.p;
         p.key = c->key;
@@ -347,7 +370,12 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
         p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
-        p.ll_part = c->ll.p; p.ll_red = c->ll.p + (size_t)c->nW * c->PS * 2; p.ll_bcast = p.ll_red + (size_t)c->PS * 2; p.ll_delta = p.ll_bcast + (size_t)c->PS * 2; p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
+        p.ll_part = c->ll.p; p.ll_bcast = p.ll_part + (size_t)c->nW * c->PS * 2; p.ll_delta = p.ll_bcast + (size_t)c->PS * 2;
+        p.ll_fin = p.ll_delta + ((size_t)2 * c->PS + 1) * 2;
+        p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
+        p.rank = c->win.rank; p.R = c->win.R;
+        for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
+        p.xphase0 = (uint32_t)((uint64_t)it * (uint64_t)(c->nb + (F > 0 ? 1 : 0)));
         p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
@@ -357,7 +385,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         h.kind = c->kind; h.it = it; h.n_total = g->n_total; h.M = M; h.K = K; h.G = G; h.F = F;
         h.v0E = c->v0E; h.s02E = c->s02E; h.v0G = c->v0G; h.s02G = c->s02G;
         h.sc = c->sc.p; h.sigmaG = c->sigmaG.p; h.pi = c->pi.p; h.vcount = c->vcount.p; h.betaAcum = c->betaAcum.p;
-        h.beta = c->beta.p; h.alpha = c->alpha.p; h.fin = c->fin.p; h.nW = c->nW; h.key = c->key;
+        h.beta = c->beta.p; h.alpha = c->alpha.p; h.fin = c->fin.p; h.nW = 1; h.key = c->key;
         const bool next_in = rp && it + 1 < c->rp_iters;
         h.tbl_gam = rp && c->rp_gam.p ? c->rp_gam.p + (size_t)it * c->rp_ngam : nullptr;
         h.tbl_gam_next = next_in && c->rp_gam.p ? c->rp_gam.p + (size_t)(it + 1) * c->rp_ngam : nullptr;
@@ -376,6 +404,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     }
     BRR_CUDA(cudaEventRecord(c->ev1, c->stream));
     BRR_CUDA(cudaStreamSynchronize(c->stream));
+    if (sharded) { double token = 1.0; comm_allreduce(c->comm, &token, 1); }    // no rank leaves while a peer may still be copying its residuals
     {
         int flag = 0;
         BRR_CUDA(cudaMemcpy(&flag, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -407,15 +436,21 @@ void check_iters(int max_iterations, int burn_in, int thinning)
 }  // namespace
 
 // =================================================================================================
-extern "C" int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **out)
+static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm *comm, brr_chain **out)
 {
     return guarded([&] {
         BRR_REQUIRE(cfg && g && out, BRR_E_ARG, "brr_chain_create: null pointer");
+        if (comm) {
+            BRR_REQUIRE(comm->world >= 1 && comm->world <= BRR_MAX_WORLD && comm->rank >= 0 && comm->rank < comm->world, BRR_E_SIZE,
+                        "brr_comm: world must be in [1, " + std::to_string(BRR_MAX_WORLD) + "] and rank in [0, world)");
+            BRR_REQUIRE(comm->world == 1 || (comm->allreduce_sum && comm->allgather), BRR_E_ARG, "brr_comm: call-backs missing");
+        }
         BRR_REQUIRE(cfg->kind >= BRR_V2 && cfg->kind <= BRR_HORSESHOE, BRR_E_ARG, "unknown sampler kind");
         check_iters(cfg->max_iterations, cfg->burn_in, cfg->thinning);
         require_device(g->device);
         std::unique_ptr<brr_chain> c(new brr_chain());
         c->g = g; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
+        if (comm) c->comm = *comm;
         c->seed = cfg->seed; c->key = PhiloxKey{ (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32) };
         c->max_iterations = cfg->max_iterations; c->burn_in = cfg->burn_in; c->thinning = cfg->thinning;
         c->sigma0 = cfg->sigma0; c->v0E = cfg->v0E; c->s02E = cfg->s02E; c->v0G = cfg->v0G; c->s02G = cfg->s02G;
@@ -457,10 +492,34 @@ extern "C" int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **
             }
         }
         choose_geometry(c.get(), cfg->block, cfg->workers);
+        const int R = c->comm.world;
+        if (R > 1) {   // every rank must cut the chain into the same Gibbs blocks: agree on the smallest block any rank chose
+            std::vector<double> bs(R, 0.0);
+            bs[c->comm.rank] = (double)c->B;
+            comm_allreduce(c->comm, bs.data(), R);
+            const int bmin = (int)*std::min_element(bs.begin(), bs.end());
+            if (bmin != c->B) choose_geometry(c.get(), bmin, cfg->workers);
+            BRR_REQUIRE(c->B == bmin, BRR_E_SIZE, "ranks of a sharded chain cannot agree on a Gibbs block size");
+        }
+        c->win.rank = c->comm.rank; c->win.R = R;
+        c->win.layout(c->PS, c->nb, c->B, g->Npad);
+        c->win.allocate();
+        c->win.connect(c->comm, g->device, g->N, c->B, c->kind, c->M);
+        c->N_total = c->win.n_total;
+        c->d_eps = c->win.eps(c->win.rank);
+        if (R > 1) BRR_REQUIRE((double)c->N_total == g->n_total, BRR_E_ARG,
+                               "the genotype store of a sharded chain needs brr_geno_shard_stats first (its statistics must cover all ranks' rows)");
         BRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         BRR_CUDA(cudaEventCreate(&c->ev0)); BRR_CUDA(cudaEventCreate(&c->ev1));
         *out = c.release();
     });
+}
+
+extern "C" int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **out) { return chain_create_impl(cfg, g, nullptr, out); }
+extern "C" int brr_chain_create_sharded(const brr_config *cfg, brr_geno *g, const brr_comm *comm, brr_chain **out)
+{
+    if (!comm) { set_last_error("brr_chain_create_sharded: comm is null"); return BRR_E_ARG; }
+    return chain_create_impl(cfg, g, comm, out);
 }
 
 extern "C" int brr_chain_set_replay(brr_chain *c, const brr_replay *r)

@@ -59,4 +59,6 @@ struct brr_geno {
 namespace brr {
 // recompute xsq / csum (device + host mirrors) from a, d, S, Q
 void geno_finalize_stats(brr_geno *g);
+// recompute a, d from S, Q and n_total (sd with the n_total - 1 denominator), then xsq / csum
+void geno_affine_from_stats(brr_geno *g);
 }

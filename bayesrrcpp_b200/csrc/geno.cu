@@ -255,6 +255,14 @@ void geno_finalize_stats(brr_geno *g)
     BRR_CUDA(cudaMemcpy(g->h_xsq.data(), g->d_xsq, M * 8, cudaMemcpyDeviceToHost));
 }
 
+void geno_affine_from_stats(brr_geno *g)
+{
+    const int64_t M = g->M;
+    affine_from_stats_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, g->n_total, g->d_S, g->d_Q, nullptr, nullptr, g->d_a, g->d_d);
+    BRR_CUDA(cudaGetLastError());
+    geno_finalize_stats(g);
+}
+
 static brr_geno *geno_alloc(int64_t N, int64_t M, int device)
 {
     BRR_REQUIRE(N >= 2 && M >= 1, BRR_E_ARG, "genotype matrix needs N >= 2 rows and M >= 1 markers");

@@ -6,6 +6,7 @@ namespace brr {
 
 constexpr int SWEEP_THREADS = 256;
 constexpr int KMAX = 16;          // mixture components supported by the in-block sampler
+constexpr int MAXR = BRR_MAX_WORLD;   // ranks of a row-sharded chain
 
 // Scalars of the chain that live on the device between kernels.
 struct IterScalars {
@@ -56,12 +57,18 @@ struct SweepParams {
     const double *tbl_fix_z;      // F or null
     // grid protocol
     uint64_t *ll_part;            // PS x nW flagged-word slots (2 x u64 each), column-major: workers' partial dots; zeroed before launch
-    uint64_t *ll_red;             // PS slots: column totals, reducer warps -> sampler; zeroed before launch
+    // cross-rank exchange over peer memory (row-sharded chains; R == 1: this device's own window).  Never zeroed between
+    // launches: flags are global phase numbers, monotone over the life of the chain.
+    int rank, R;
+    uint64_t *xred[MAXR];         // every rank's window of column totals: [2 phase parities][PS][R] slots; this rank writes [.][.][rank]
+    uint64_t *xfin[MAXR];         // every rank's window of end-of-sweep sums: [R][2] slots (sum eps, sum eps^2 over that rank's rows)
+    uint32_t xphase0;             // global number of this launch's first phase
+    uint64_t *ll_fin;             // nW x 2 slots: workers' sum eps, sum eps^2 -> sampler; zeroed before launch
     uint64_t *ll_delta;           // PS slots: the sampler's per-marker deltas of the current block, streamed as they are decided
     uint64_t *ll_bcast;           // (3 x PS + 1) slots: sampler -> workers delta, a*delta, d*delta (+ sentinel); zeroed before launch
     long long *prof;              // optional cycle accounting of the sampler CTA: wait, reduce, pass, publish, windows, full steps, blocks
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
-    double *fin;                  // nW x 2: sum eps, sum eps^2 over the worker's rows
+    double *fin;                  // 2: sum eps, sum eps^2 over ALL rows (all ranks), written by the sampler CTA
     int nW; int PS;
     const int32_t *unit0;         // nW + 1: first 64-row unit of every worker
     int seg_bytes;                // bytes reserved per staged column segment (max units * 16)

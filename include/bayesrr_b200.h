@@ -83,7 +83,7 @@ int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_bytes, int64_
                          const double *mean, const double *sd, int device, brr_geno **out);
 /* Device-side synthetic generator: g_ij ~ Binomial(2, p_j), p_j ~ U(0.05, 0.5), standardised.
  * Row sharding: this store holds rows [row0, row0+N) of a virtual N_total-row matrix (statistics are
- * computed over the local rows only unless brr_geno_set_stats is called).                       */
+ * computed over the local rows only until brr_geno_shard_stats is called).                      */
 int brr_geno_synthetic(int64_t N, int64_t M, uint64_t seed, int64_t row0, int device, brr_geno **out);
 int brr_geno_dims(const brr_geno *g, int64_t *N, int64_t *M, int64_t *col_stride_bytes);
 /* host copies of the per-SNP statistics (any pointer may be NULL): code mean, code sd, a, d, ||x||^2 */
@@ -161,6 +161,37 @@ int brr_chain_geometry(const brr_chain *c, int *block, int *workers, int *rows_p
 /* flush the writer and close the output file */
 int brr_chain_close_output(brr_chain *c);
 void brr_chain_destroy(brr_chain *c);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-sharded chains: the individuals (rows of X, Y, fixed, epsilon) are partitioned over `world` devices,
+ * one rank per device (one process per GPU, or several ranks as threads of one process).  Every rank runs
+ * the whole chain (beta, components, pi, sigma replicated and bit-identical); per Gibbs block the ranks'
+ * partial X_b^T eps vectors are exchanged device-to-device over NVLink peer memory inside the persistent
+ * sweep kernel and summed in rank order, and the per-iteration Gram partials are summed by a peer-memory
+ * kernel.  The host supplies two collectives, used at set-up time and at the
+ * run boundaries only (never inside the iteration loop):
+ * ------------------------------------------------------------------------------------------------ */
+enum { BRR_MAX_WORLD = 8 };
+typedef struct brr_comm {
+    int rank, world;
+    /* in-place sum over ranks of buf[0..n); every rank must end with identical bits; returns 0 on success */
+    int (*allreduce_sum)(void *ctx, double *buf, int64_t n);
+    /* recv (world * nbytes) = concatenation of every rank's send (nbytes) in rank order; returns 0 on success */
+    int (*allgather)(void *ctx, const void *send, void *recv, int64_t nbytes);
+    void *ctx;                      /* must stay valid for the life of the objects created with this comm */
+} brr_comm;
+
+/* Replace the per-SNP statistics (mean, sd, a, d, ||x||^2) of a row shard by those of the whole matrix
+ * (code sums allreduced over the ranks; sd with the N_total - 1 denominator).  Collective. */
+int brr_geno_shard_stats(brr_geno *g, const brr_comm *comm);
+/* Like brr_chain_create for a row shard: cfg->Y / fixed / epsilon0 hold this rank's rows, everything indexed by
+ * marker is replicated.  `g` must have had brr_geno_shard_stats applied.  Sample rows carry the residuals of
+ * ALL ranks (reference row layout with N = N_total) on every rank.  Collective; so are brr_chain_run and
+ * brr_chain_destroy of a sharded chain. */
+int brr_chain_create_sharded(const brr_config *cfg, brr_geno *g, const brr_comm *comm, brr_chain **out);
+/* exercises the two call-backs (CPU only: no device needed): buf[0..n) is sum-allreduced, gathered[world] receives
+ * every rank's `token` */
+int brr_comm_selftest(const brr_comm *comm, double *buf, int64_t n, int64_t token, int64_t *gathered);
 
 /* Stand-alone kernels exposed for parity tests and roofline measurement.
  * gram: G[b][i][j] = sum_n code[n, order[b*B+i]] * code[n, order[b*B+j]]  (int32, nb x B x B; order index -1 = padding) */
