@@ -3,7 +3,9 @@
 
 A "step" is one Gibbs iteration: one pass of the hot path (block Gram -> persistent sweep -> hyper draws) over all M
 markers.  N=1 workload = BASELINE.json configs[1]: BayesRSamplerV2, N=50,000 x M=50,000 synthetic genotypes, simulated
-phenotype h2=0.5, K=4.  Rank r of a multi-GPU run holds its own N-row shard (weak scaling, see DESIGN.md "Multi-GPU").
+phenotype h2=0.5, K=4.  A multi-GPU run is ONE chain over N_total = 50,000 x world individuals, row-sharded: rank r holds
+rows [50,000 r, 50,000 (r+1)) of the same virtual matrix (weak scaling: fixed rows per GPU), every rank replicates the chain,
+the per-block partial dots are exchanged over NVLink peer memory inside the sweep kernel.
 
   value     : whole-job SNP-updates/s, genotypes resident in HBM, device-timed (CUDA events on the chain's stream)
   e2e       : same metric through the C ABI with HOST buffers: packed genotypes H2D, chain creation, per-iteration
@@ -81,14 +83,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def simulate_phenotype(geno, seed, h2, causal_frac):
+def simulate_phenotype(geno, seed, h2, causal_frac, rank=0, allreduce=None):
+    """y = X b + e over this rank's rows (same effects b on every rank), centred and scaled over ALL rows"""
     rng = np.random.default_rng(seed)
     M, N = geno.M, geno.N
     mc = max(1, int(round(causal_frac * M)))
     b = np.zeros(M)
     b[rng.choice(M, mc, replace=False)] = rng.normal(0, np.sqrt(h2 / mc), size=mc)
-    y = geno.matvec(b) + rng.normal(0, np.sqrt(1 - h2), size=N)
-    return (y - y.mean()) / y.std(ddof=1)
+    y = geno.matvec(b) + np.random.default_rng(seed + 104729 * (rank + 1)).normal(0, np.sqrt(1 - h2), size=N)
+    mom = np.array([float(N), y.sum(), (y * y).sum()])
+    if allreduce is not None:
+        allreduce(mom)
+    mean = mom[1] / mom[0]
+    sd = np.sqrt((mom[2] - mom[0] * mean * mean) / (mom[0] - 1))
+    return (y - mean) / sd
 
 
 def cpu_sample_data(N, M_s, seed):
@@ -151,17 +159,26 @@ def main():
 
     import torch
     import bayesrrcpp_b200 as brr
-    dist = None
+    dist, comm, host_allreduce = None, None, None
     if world > 1:
         import torch.distributed as dist
+        from bayesrrcpp_b200 import sharded
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = sharded.torch_comm()                    # gloo group for the library's host call-backs (set-up time only)
+
+        def host_allreduce(a):
+            t = torch.from_numpy(a).cuda()             # NCCL over NVLink
+            dist.all_reduce(t)
+            a[:] = t.cpu().numpy()
     dev = local
-    N, M = CFG["N"], CFG["M"]
-    geno = brr.Genotypes.synthetic(N, M, CFG["data_seed"] + 7919 * rank, device=dev)
-    y = simulate_phenotype(geno, CFG["data_seed"] + rank, CFG["h2"], CFG["causal_frac"])
+    N, M = CFG["N"], CFG["M"]                          # N: rows per GPU
+    geno = brr.Genotypes.synthetic(N, M, CFG["data_seed"], row0=rank * N, device=dev)
+    if comm is not None:
+        geno.shard_stats(comm)
+    y = simulate_phenotype(geno, CFG["data_seed"], CFG["h2"], CFG["causal_frac"], rank, host_allreduce)
     total_iters = args.burn + W + args.steps
-    chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"] + rank, Y=y, cva=CFG["cva"], block=args.block, **CFG["hyp"])
+    chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, comm=comm, **CFG["hyp"])
     chain.run_discard(args.burn)           # untimed chain burn-in: the timed steps see a settled sparsity pattern
     chain.run_discard(W)                           # warm-up steps
 
@@ -189,23 +206,27 @@ def main():
     if not args.no_e2e:
         codes = geno.codes()                                           # host packed genotypes (outside the timed region)
         st = geno.stats()
-        thin = 10
+        thin = 5
         tmp = tempfile.NamedTemporaryFile(suffix=".csv", delete=False); tmp.close()
         barrier()
         t0 = time.perf_counter()
         g2 = brr.Genotypes.from_packed(codes, N, mean=st["mean"], sd=st["sd"], device=dev)    # H2D of the packed matrix
-        c2 = brr.Chain(g2, brr.V2, args.steps, burn_in=1, thinning=thin, seed=CFG["chain_seed"] + rank, Y=y, cva=CFG["cva"],
-                       block=args.block, **CFG["hyp"])
-        c2.open_output(tmp.name)
+        if comm is not None:
+            g2.shard_stats(comm)
+        c2 = brr.Chain(g2, brr.V2, args.steps, burn_in=1, thinning=thin, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"],
+                       block=args.block, comm=comm, **CFG["hyp"])
+        if rank == 0:
+            c2.open_output(tmp.name)
         kept = c2.run_discard(args.steps)                              # perm H2D per step, kept rows D2H + CSV writer
-        c2.close_output()
+        if rank == 0:
+            c2.close_output()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % dev)
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
-        row_bytes = 8 * (2 * M + 4 + N)
+        row_bytes = 8 * (2 * M + 4 + N * world)
         e2e = {"value": world * M * args.steps / dt, "unit": "SNP-updates/s",
                "h2d_bytes_per_step": int(codes.nbytes / args.steps + 4 * M + 8 * N / args.steps),
                "d2h_bytes_per_step": int(row_bytes * kept / args.steps),
@@ -219,7 +240,7 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    algo_bytes = M * ((N + 3) // 4) + 16 * N + 24 * M                  # per sweep launch
+    algo_bytes = M * ((N + 3) // 4) + 16 * N + 24 * M                  # per sweep launch and GPU
     sweep_ms = kms["sweep"] / args.steps
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
     out = {"metric": "SNP-updates/sec", "value": value, "unit": "SNP-updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -228,8 +249,15 @@ def main():
            "config": {"workload": WORKLOAD, "block": geom["block"], "workers": geom["workers"],
                       "rows_per_worker_max": geom["rows_per_worker_max"], "chain_burn_in_iterations": args.burn,
                       "l2": "inputs larger than L2: 625 MB of packed genotypes are re-read every step",
-                      "parallelism": "1 GPU" if world == 1 else "%d independent row shards (replicas; no exchange yet)" % world,
-                      "gibbs_iterations_per_s": world * 1e3 * args.steps / ms_max if world == 1 else 1e3 * args.steps / ms_max},
+                      "parallelism": "1 GPU" if world == 1 else
+                      "ONE chain over N_total=%d individuals, row-sharded over %d GPUs (%d rows each), chain replicated, per-block "
+                      "exchange of partial dots over NVLink peer memory inside the sweep kernel" % (N * world, world, N),
+                      "n_total": N * world,
+                      "value_definition": "SNP-updates/s in units of one marker update over one GPU's 50,000-row shard: world x M x steps / time "
+                                          "(weak scaling in individuals; the chain itself advances chain_snp_updates_per_s markers per second)",
+                      "chain_snp_updates_per_s": M * args.steps / (ms_max * 1e-3),
+                      "genotype_cells_per_s": float(N) * world * M * args.steps / (ms_max * 1e-3),
+                      "gibbs_iterations_per_s": 1e3 * args.steps / ms_max},
            "gpu_launches": int(launches),
            "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
            "cycles_per_block": {k: prof[k] / max(prof["blocks"], 1) for k in ("gather", "serial_pass", "publish", "prepass", "bookkeeping", "chunks_received", "worker_wait", "worker_dots", "worker_reduce")},
