@@ -51,7 +51,7 @@ struct brr_chain {
     brr_comm comm{0, 1, nullptr, nullptr, nullptr};
     Window win;                                                   // exchange window (holds eps; peers write / read it when sharded)
     double *d_eps = nullptr;                                      // = win.eps(rank)
-    DevBuf<int32_t> gram_part_unused;
+    DevBuf<uint8_t> gtab;                                         // per-marker tables of the current iteration (tables_kernel)
     uint64_t seed = 0; PhiloxKey key{0, 0};
     int max_iterations = 0, burn_in = 0, thinning = 1;
     double sigma0 = 0, v0E = 0, s02E = 0, v0G = 0, s02G = 0;
@@ -256,6 +256,7 @@ void chain_init(brr_chain *c)
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
     c->gram.alloc((size_t)c->nb * c->B * c->B);
+    c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
         c->h_perm[i].alloc(pn); c->d_perm[i].alloc(pn);
@@ -377,6 +378,8 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
         p.xphase0 = (uint32_t)((uint64_t)it * (uint64_t)(c->nb + (F > 0 ? 1 : 0)));
         p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
+        p.gtab = c->gtab.p;
+        launch_tables(kk, c->B, p, c->gtab.p, c->stream);
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
         BRR_CUDA(cudaEventRecord(c->perm_free[slot], c->stream));
@@ -396,7 +399,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         h.tbl_hs_nu_next = next_in && c->rp_nu.p ? c->rp_nu.p + (size_t)(it + 1) * M : nullptr;
         launch_hyper(h, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 3], c->stream));
-        launches += 2 + hyper_launch_count(c->kind);
+        launches += 3 + hyper_launch_count(c->kind);
 
         if (emit_all || (it >= c->burn_in && it % c->thinning == 0))                     // :257-259
             snapshot_row(c, it, rows, max_rows, n_rows);

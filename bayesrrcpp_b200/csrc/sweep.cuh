@@ -29,6 +29,7 @@ struct SweepParams {
     // iteration inputs
     const int32_t *perm;          // M markers in visiting order
     const int32_t *gram;          // nb x B x B int32 (codes), rows/cols in visiting order
+    const uint8_t *gtab;          // nb x table bytes: per-marker tables of this iteration (tables_kernel), sampler smem layout
     int64_t M; int nb;
     int64_t it;
     // chain state
@@ -78,6 +79,9 @@ struct SweepParams {
 struct SweepGeom { int B, TW, nW, seg_bytes; size_t smem_bytes; };
 
 void launch_sweep(int kind, int B, int TW, const SweepParams &p, size_t smem, cudaStream_t stream);
+// per-marker tables of the iteration described by `p` into gtab (nb x sweep_table_bytes); kind as for launch_sweep
+void launch_tables(int kind, int B, const SweepParams &p, uint8_t *gtab, cudaStream_t stream);
+size_t sweep_table_bytes(int kind, int B, int K, int G, int F);
 size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
