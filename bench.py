@@ -240,6 +240,13 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    traffic = None                                  # DRAM bytes of one sweep launch from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v3.json")) as f:
+            k = [v for n, v in json.load(f).items() if "sweep_kernel" in n][0]
+            traffic = int(1e6 * (float(k["dram__bytes_read.sum"]["value"]) + float(k["dram__bytes_write.sum"]["value"])))
+    except Exception:
+        pass
     algo_bytes = M * ((N + 3) // 4) + 16 * N + 24 * M                  # per sweep launch and GPU
     sweep_ms = kms["sweep"] / args.steps
     achieved = algo_bytes / (sweep_ms * 1e-3) / 1e9
@@ -264,7 +271,7 @@ def main():
            "markers_per_speculative_window": (M * args.steps) / max(prof["windows"], 1),
            "state_changing_marker_fraction": prof["full_steps"] / (M * args.steps),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "kernel": "sweep_kernel", "peak_source": peak_src,
+                        "traffic": traffic, "algorithmic_bytes": algo_bytes, "kernel": "sweep_kernel", "peak_source": peak_src,
                         "note": "serial Gibbs chain: the kernel is latency-bound (M dependent marker steps), see DESIGN.md 4"},
            "clocks": clk.summary()}
     if e2e:
