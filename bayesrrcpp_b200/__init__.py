@@ -158,6 +158,16 @@ class Genotypes:
                                      G.ctypes.data_as(_ip), C.byref(ms)))
         return G, ms.value
 
+    def gram_cross_blocks(self, order, block=128, impl=0):
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        nb = (len(order) + block - 1) // block
+        G = np.zeros((nb, block, block), dtype=np.int32)
+        X = np.zeros((nb, 32, block), dtype=np.int32)
+        ms = C.c_double()
+        _check(lib().brr_gram_cross_blocks(self._h, order.ctypes.data_as(_ip), C.c_int64(len(order)), C.c_int(block), C.c_int(impl),
+                                           G.ctypes.data_as(_ip), X.ctypes.data_as(_ip), C.byref(ms)))
+        return G, X, ms.value
+
     def close(self):
         if self._h:
             lib().brr_geno_free(self._h)

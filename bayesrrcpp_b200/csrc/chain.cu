@@ -351,10 +351,10 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
 
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
         if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
-            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->win.gram(c->win.rank), c->stream);
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->win.gram(c->win.rank), nullptr, c->stream);
             launch_gram_allsum(c->win, (uint32_t)it + 1u, c->gram.p, (size_t)c->nb * c->B * c->B, c->abort_flag.p, c->stream);
             ++launches;
-        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->stream);
+        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, nullptr, c->stream);
         c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 

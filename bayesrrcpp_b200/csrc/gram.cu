@@ -11,9 +11,12 @@
 
 namespace brr {
 
-constexpr int GRAM_KC = 512;                       // rows (K) per pipeline stage
-constexpr int GRAM_STAGE_ROW = GRAM_KC / 4 + 16;   // bytes per staged packed column (padded: conflict-free 128-bit reads)
-constexpr int GRAM_TILE_BYTES = 128 * GRAM_KC;     // int8 operand tile: 128 marker rows x KC
+constexpr int GRAM_KC = 256;                       // rows (K) per operand tile (one commit group of MMAs)
+constexpr int GRAM_LDR = 1024;                     // rows per load stage: ONE 256-byte bulk copy per marker (bulk copies have a fixed
+                                                   // issue cost of tens of cycles each; 128-byte copies left the kernel copy-issue bound)
+constexpr int GRAM_LA = 32;                        // look-ahead markers: the last GRAM_LA markers of the previous block (cross products)
+constexpr int GRAM_STAGE_ROW = GRAM_LDR / 4 + 16;  // bytes per staged packed column (padded: conflict-free 128-bit reads)
+constexpr int GRAM_TILE_BYTES = (128 + GRAM_LA) * GRAM_KC;   // int8 operand tile: up to 128 + 32 marker rows x KC
 constexpr int GRAM_SBO = (GRAM_KC / 16) * 128;     // byte stride between 8-marker groups
 constexpr int GRAM_LBO = 128;                      // byte stride between K-adjacent 8x16B core matrices
 
@@ -64,36 +67,40 @@ __device__ __forceinline__ uint4 expand16(uint32_t w)
     return r;
 }
 
-template <int B>
+// CROSS: additionally X[blk][jl][k] = sum_n code[n, order[blk*B - 32 + jl]] * code[n, order[blk*B + k]] -- the products of the
+// block's markers with the last 32 markers of the previous block (the look-ahead correction of the sweep):
+// those 32 markers are 32 more rows of the B operand (N = B + 32 columns of the accumulator), the A operand is unchanged.
+template <int B, bool CROSS>
 __global__ void __launch_bounds__(256, 1)
 gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
-               const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G)
+               const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G, int32_t *__restrict__ X)
 {
     static_assert(B == 32 || B == 64 || B == 128, "block size");
+    constexpr int R = CROSS ? B + GRAM_LA : B;              // marker rows of the operand tile
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tile0 = smem;                                  // 2 x 64 KB operand tiles
-    uint8_t *stage0 = smem + 2 * GRAM_TILE_BYTES;           // 2 x B x GRAM_STAGE_ROW staged packed columns
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + 2 * B * GRAM_STAGE_ROW);   // full[2], free[2]
+    uint8_t *stage0 = smem + 2 * GRAM_TILE_BYTES;           // 2 x R x GRAM_STAGE_ROW staged packed columns
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + 2 * R * GRAM_STAGE_ROW);   // full[2], free[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-    int32_t *cols = reinterpret_cast<int32_t *>(tmem_slot + 2);                        // B marker ids
+    int32_t *cols = reinterpret_cast<int32_t *>(tmem_slot + 2);                        // R marker ids
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int64_t blk = blockIdx.x;
     uint64_t *full = bars, *freeb = bars + 2;
 
-    if (tid < B) {
-        const int64_t o = blk * B + tid;
-        cols[tid] = o < n_order ? order[o] : -1;
+    if (tid < R) {
+        const int64_t o = tid < B ? blk * B + tid : blk * B - GRAM_LA + (tid - B);   // rows B.. : tail of the previous block
+        cols[tid] = (o >= 0 && o < n_order && (tid < B || blk > 0)) ? order[o] : -1;
     }
-    // zero both operand tiles (rows of padding markers and rows >= B must read as 0) and both stages
-    for (int i = tid; i < (2 * GRAM_TILE_BYTES + 2 * B * GRAM_STAGE_ROW) / 16; i += 256)
+    // zero both operand tiles (rows of padding markers and rows >= R must read as 0) and both stages
+    for (int i = tid; i < (2 * GRAM_TILE_BYTES + 2 * R * GRAM_STAGE_ROW) / 16; i += 256)
         reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&freeb[0], 1); mbar_init(&freeb[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: 128 lanes x 128 int32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (warp == 0) {   // TMEM: 128 lanes x 256 int32 columns (B + 32 used)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -102,63 +109,70 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    const int nchunks = (int)(Npad / GRAM_KC);
+    const int nloads = (int)((Npad + GRAM_LDR - 1) / GRAM_LDR);
     int nvalid = 0;
-    for (int c = 0; c < B; ++c) nvalid += cols[c] >= 0;
+    for (int c = 0; c < R; ++c) nvalid += cols[c] >= 0;
 
-    auto issue_loads = [&](int chunk) {   // called by threads < B after thread 0's expect_tx; one 128-byte bulk copy per marker
-        const int s = chunk & 1;
-        if (tid == 0) mbar_expect_tx(&full[s], (uint32_t)nvalid * (GRAM_KC / 4));
-        if (tid < B && cols[tid] >= 0)
-            bulk_g2s(stage0 + (s * B + tid) * GRAM_STAGE_ROW, packed + (int64_t)cols[tid] * stride + (int64_t)chunk * (GRAM_KC / 4),
-                     GRAM_KC / 4, &full[s]);
+    auto load_rows = [&](int L) { const int64_t left = Npad - (int64_t)L * GRAM_LDR; return (int)(left < GRAM_LDR ? left : GRAM_LDR); };
+    auto issue_loads = [&](int L) {   // one bulk copy per marker: its rows [L * LDR, L * LDR + load_rows)
+        const int s = L & 1;
+        const uint32_t bytes = (uint32_t)load_rows(L) / 4;
+        if (tid == 0) mbar_expect_tx(&full[s], (uint32_t)nvalid * bytes);
+        if (tid < R && cols[tid] >= 0)
+            bulk_g2s(stage0 + (s * R + tid) * GRAM_STAGE_ROW, packed + (int64_t)cols[tid] * stride + (int64_t)L * (GRAM_LDR / 4), bytes, &full[s]);
     };
     if (nvalid == 0) {   // nothing to do but keep the protocol simple: write zeros
         for (int i = tid; i < B * B; i += 256) G[blk * B * B + i] = 0;
+        if (CROSS) for (int i = tid; i < GRAM_LA * B; i += 256) X[blk * GRAM_LA * B + i] = 0;
     } else {
         issue_loads(0);
-        if (nchunks > 1) issue_loads(1);
+        if (nloads > 1) issue_loads(1);
         // instruction descriptor: D = S32, A = B = unsigned 8-bit, both K-major, N = B, M = 128
-        constexpr uint32_t idesc = (2u << 4) | ((uint32_t)(B >> 3) << 17) | ((128u >> 4) << 24);
-        for (int i = 0; i < nchunks; ++i) {
-            const int s = i & 1;
-            mbar_wait(&full[s], (uint32_t)((i >> 1) & 1));
-            if (i >= 2) mbar_wait(&freeb[s], (uint32_t)(((i >> 1) - 1) & 1));
-            uint8_t *tile = tile0 + s * GRAM_TILE_BYTES;
-            const uint8_t *stage = stage0 + s * B * GRAM_STAGE_ROW;
-            // unpack: item = (v, c): 64 rows of marker c -> four 16-byte core-matrix rows
-            for (int item = tid; item < B * (GRAM_KC / 64); item += 256) {
-                const int c = item % B, v = item / B;
-                const uint4 q = *reinterpret_cast<const uint4 *>(stage + c * GRAM_STAGE_ROW + v * 16);
-                uint8_t *dst = tile + (c >> 3) * GRAM_SBO + (c & 7) * 16 + (v * 4) * GRAM_LBO;
-                *reinterpret_cast<uint4 *>(dst) = expand16(q.x);
-                *reinterpret_cast<uint4 *>(dst + GRAM_LBO) = expand16(q.y);
-                *reinterpret_cast<uint4 *>(dst + 2 * GRAM_LBO) = expand16(q.z);
-                *reinterpret_cast<uint4 *>(dst + 3 * GRAM_LBO) = expand16(q.w);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-            __syncthreads();
-            if (i + 2 < nchunks) issue_loads(i + 2);                        // stage s is free again
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t base = smem_u32(tile);
-#pragma unroll 4
-                for (int kk = 0; kk < GRAM_KC / 32; ++kk) {
-                    const uint64_t da = umma_desc(base + kk * 2 * GRAM_LBO);
-                    const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(da), "l"(da), "r"(idesc), "r"(acc) : "memory");
+        constexpr uint32_t idesc = (2u << 4) | ((uint32_t)(R >> 3) << 17) | ((128u >> 4) << 24);
+        int g = 0;                                   // running tile count: tile g uses operand buffer g & 1
+        for (int L = 0; L < nloads; ++L) {
+            const int s = L & 1;
+            mbar_wait(&full[s], (uint32_t)((L >> 1) & 1));
+            const uint8_t *stage = stage0 + s * R * GRAM_STAGE_ROW;
+            const int nsub = load_rows(L) / GRAM_KC;
+            for (int sub = 0; sub < nsub; ++sub, ++g) {
+                const int ts = g & 1;
+                if (g >= 2) mbar_wait(&freeb[ts], (uint32_t)(((g >> 1) - 1) & 1));     // the MMAs that read this buffer are done
+                uint8_t *tile = tile0 + ts * GRAM_TILE_BYTES;
+                // unpack: item = (v, c): 64 rows of marker c -> four 16-byte core-matrix rows
+                for (int item = tid; item < R * (GRAM_KC / 64); item += 256) {
+                    const int c = item % R, v = item / R;
+                    const uint4 q = *reinterpret_cast<const uint4 *>(stage + c * GRAM_STAGE_ROW + (sub * (GRAM_KC / 64) + v) * 16);
+                    uint8_t *dst = tile + (c >> 3) * GRAM_SBO + (c & 7) * 16 + (v * 4) * GRAM_LBO;
+                    *reinterpret_cast<uint4 *>(dst) = expand16(q.x);
+                    *reinterpret_cast<uint4 *>(dst + GRAM_LBO) = expand16(q.y);
+                    *reinterpret_cast<uint4 *>(dst + 2 * GRAM_LBO) = expand16(q.z);
+                    *reinterpret_cast<uint4 *>(dst + 3 * GRAM_LBO) = expand16(q.w);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(smem_u32(&freeb[s])) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                __syncthreads();
+                if (sub == nsub - 1 && L + 2 < nloads) issue_loads(L + 2);      // every thread is past its last read of stage s
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t base = smem_u32(tile);
+#pragma unroll
+                    for (int kk = 0; kk < GRAM_KC / 32; ++kk) {
+                        const uint64_t da = umma_desc(base + kk * 2 * GRAM_LBO);
+                        const uint32_t acc = (g > 0 || kk > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem), "l"(da), "l"(da), "r"(idesc), "r"(acc) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 ::"r"(smem_u32(&freeb[ts])) : "memory");
+                }
             }
         }
-        {   // all MMAs done?
-            const int last = nchunks - 1;
+        {   // all MMAs done?  (commit groups complete in order: the last two cover both buffers)
+            const int last = g - 1;
             mbar_wait(&freeb[last & 1], (uint32_t)((last >> 1) & 1));
-            if (nchunks > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1)); }
+            if (g > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1)); }
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // epilogue: TMEM lane = marker row i, column = marker j
@@ -184,11 +198,29 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                     for (int q = 0; q < 8; ++q) dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
                 }
             }
+            if (CROSS) {   // accumulator columns B .. B + 31: products with the previous block's tail, stored [jl][k]
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)B;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < B) {
+#pragma unroll
+                    for (int jl = 0; jl < 32; ++jl) X[(blk * GRAM_LA + jl) * B + row] = (int)v[jl];
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 // ---- CUDA-core reference: 8 x 8 register tile per thread, dp4a over int8-expanded codes.
@@ -239,11 +271,36 @@ __global__ void __launch_bounds__(256) gram_dp4a_kernel(const uint8_t *__restric
         }
 }
 
-template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * B * GRAM_STAGE_ROW + 4 * 8 + 8 + B * 4 + 64; }
+// ---- CUDA-core reference of the cross products (validation): bit-sliced, a*b = lo_a lo_b + 2 lo_a hi_b + 2 hi_a lo_b + 4 hi_a hi_b
+__global__ void __launch_bounds__(256) cross_bits_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
+                                                         const int32_t *__restrict__ order, int64_t n_order, int B,
+                                                         int32_t *__restrict__ X)
+{
+    const int64_t blk = blockIdx.x;
+    const int64_t nwords = Npad / 16;
+    for (int pair = threadIdx.x; pair < GRAM_LA * B; pair += blockDim.x) {
+        const int jl = pair / B, k = pair % B;
+        const int64_t oj = blk * B - GRAM_LA + jl, ok = blk * B + k;
+        int32_t acc = 0;
+        if (blk > 0 && oj >= 0 && ok < n_order && order[oj] >= 0 && order[ok] >= 0) {
+            const uint32_t *a = reinterpret_cast<const uint32_t *>(packed + (int64_t)order[oj] * stride);
+            const uint32_t *b = reinterpret_cast<const uint32_t *>(packed + (int64_t)order[ok] * stride);
+            for (int64_t w = 0; w < nwords; ++w) {
+                const uint32_t x = a[w], y = b[w];
+                const uint32_t xl = x & 0x55555555u, xh = (x >> 1) & 0x55555555u, yl = y & 0x55555555u, yh = (y >> 1) & 0x55555555u;
+                acc += __popc(xl & yl) + 2 * (__popc(xl & yh) + __popc(xh & yl)) + 4 * __popc(xh & yh);
+            }
+        }
+        X[(blk * GRAM_LA + jl) * B + k] = acc;
+    }
+}
+
+template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + GRAM_LA) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + GRAM_LA) * 4 + 64; }
 
 // launch on `stream`; G must hold nblocks * B * B int32
-void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, cudaStream_t stream)
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream)
 {
+
     const int64_t nb = (n_order + B - 1) / B;
     if (nb == 0) return;
     BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
@@ -252,10 +309,12 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
         if (impl == 0) {                                                                                                    \
             static bool attr_set = false;                                                                                   \
             if (!attr_set) {                                                                                                \
-                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
+                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
+                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
                 attr_set = true;                                                                                            \
             }                                                                                                               \
-            gram_tc_kernel<BB><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G); \
+            if (d_X) gram_tc_kernel<BB, true><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X); \
+            else gram_tc_kernel<BB, false><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr); \
         } else {                                                                                                            \
             gram_dp4a_kernel<BB><<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G);      \
         }                                                                                                                   \
@@ -263,14 +322,18 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
     BRR_GRAM_CASE(32) BRR_GRAM_CASE(64) BRR_GRAM_CASE(128)
 #undef BRR_GRAM_CASE
     BRR_CUDA(cudaGetLastError());
+    if (impl != 0 && d_X) {
+        cross_bits_kernel<<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, B, d_X);
+        BRR_CUDA(cudaGetLastError());
+    }
 }
 
 }  // namespace brr
 
 using namespace brr;
 
-extern "C" int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
-                               int32_t *G_out, double *ms)
+extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
+                                     int32_t *G_out, int32_t *X_out, double *ms)
 {
     return guarded([&] {
         BRR_REQUIRE(g && order && G_out && n_order > 0, BRR_E_ARG, "bad arguments");
@@ -278,20 +341,28 @@ extern "C" int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t 
         for (int64_t i = 0; i < n_order; ++i)
             BRR_REQUIRE(order[i] >= -1 && order[i] < g->M, BRR_E_ARG, "order entry out of range");
         const int64_t nb = (n_order + block - 1) / block;
-        int32_t *d_order = nullptr, *d_G = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        int32_t *d_order = nullptr, *d_G = nullptr, *d_X = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
         try {
             BRR_CUDA(cudaMalloc(&d_order, n_order * 4));
             BRR_CUDA(cudaMalloc(&d_G, (size_t)nb * block * block * 4));
+            if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * GRAM_LA * block * 4));
             BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
-            launch_gram(g, d_order, n_order, block, impl, d_G, 0);   // warm-up (module load, attribute)
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0);   // warm-up (module load, attribute)
             BRR_CUDA(cudaEventRecord(e0));
-            launch_gram(g, d_order, n_order, block, impl, d_G, 0);
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0);
             BRR_CUDA(cudaEventRecord(e1));
             BRR_CUDA(cudaEventSynchronize(e1));
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;
             BRR_CUDA(cudaMemcpy(G_out, d_G, (size_t)nb * block * block * 4, cudaMemcpyDeviceToHost));
-        } catch (...) { cudaFree(d_order); cudaFree(d_G); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
-        cudaFree(d_order); cudaFree(d_G); cudaEventDestroy(e0); cudaEventDestroy(e1);
+            if (X_out) BRR_CUDA(cudaMemcpy(X_out, d_X, (size_t)nb * GRAM_LA * block * 4, cudaMemcpyDeviceToHost));
+        } catch (...) { cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
+        cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); cudaEventDestroy(e0); cudaEventDestroy(e1);
     });
+}
+
+extern "C" int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
+                               int32_t *G_out, double *ms)
+{
+    return brr_gram_cross_blocks(g, order, n_order, block, impl, G_out, nullptr, ms);
 }

@@ -85,6 +85,8 @@ size_t sweep_table_bytes(int kind, int B, int K, int G, int F);
 size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
-void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, cudaStream_t stream);
+// d_G: nb x B x B self products; d_X (nullable): nb x LOOKAHEAD x B products with the last LOOKAHEAD markers of the previous block
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream);
+constexpr int LOOKAHEAD = 32;     // markers of a block whose deltas reach the next block through the cross-Gram correction instead of the dots
 
 }  // namespace brr

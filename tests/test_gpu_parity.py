@@ -81,6 +81,26 @@ def test_gram_tensor_core_is_bit_exact(po, brr, block):
         assert np.array_equal(G_tc[b], want), "tcgen05 gram, block %d" % b
 
 
+@pytest.mark.parametrize("block", [128, 64, 32])
+def test_gram_cross_products_with_previous_block_tail(po, brr, block):
+    """look-ahead tiles: X[b][jl][k] = codes[:, order[b*B-32+jl]] . codes[:, order[b*B+k]], tensor cores == bit-sliced CUDA cores == numpy"""
+    d = po.synth(1100, 300, seed=15)
+    g = brr.Genotypes.from_dense(d["X"])
+    codes = g.unpack().astype(np.int64)
+    order = np.random.default_rng(4).permutation(g.M).astype(np.int32)
+    G_tc, X_tc, _ = g.gram_cross_blocks(order, block=block, impl=0)
+    G_cc, X_cc, _ = g.gram_cross_blocks(order, block=block, impl=1)
+    assert np.array_equal(G_tc, G_cc) and np.array_equal(X_tc, X_cc)
+    nb = (g.M + block - 1) // block
+    assert not X_tc[0].any()
+    for b in range(1, nb):
+        prev = order[b * block - 32:b * block]
+        cur = order[b * block:(b + 1) * block]
+        want = np.zeros((32, block), dtype=np.int64)
+        want[:, :len(cur)] = codes[:, prev].T @ codes[:, cur]
+        assert np.array_equal(X_tc[b], want), "block %d" % b
+
+
 def test_gram_large_rows_property(brr):
     """full-size property: diagonal of the exact Gram == sum of squared codes, symmetry, at N = 50,000"""
     g = brr.Genotypes.synthetic(50000, 256, seed=9)
