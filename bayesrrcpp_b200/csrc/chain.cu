@@ -251,11 +251,11 @@ void chain_init(brr_chain *c)
         c->fixG.from(fg); c->alpha.from(al);
     }
     std::vector<IterScalars> scv(1, sc); c->sc.from(scv);
-    c->ll.alloc(((size_t)c->nW * c->PS + 3 * (size_t)c->PS + 1 + 2 * (size_t)c->nW) * 2); c->ll.zero();
+    c->ll.alloc((2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2); c->ll.zero();
     c->fin.alloc(2); c->fin.zero();
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
-    c->gram.alloc((size_t)c->nb * c->B * c->B);
+    c->gram.alloc((size_t)c->nb * c->B * (c->B + LOOKAHEAD));      // self tiles, then the look-ahead cross tiles
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
@@ -350,11 +350,13 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         c->perm_used[slot] = true;
 
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
+        const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + LOOKAHEAD);
         if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
-            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->win.gram(c->win.rank), nullptr, c->stream);
-            launch_gram_allsum(c->win, (uint32_t)it + 1u, c->gram.p, (size_t)c->nb * c->B * c->B, c->abort_flag.p, c->stream);
+            int32_t *part = c->win.gram(c->win.rank);
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->stream);
+            launch_gram_allsum(c->win, (uint32_t)it + 1u, c->gram.p, all_ints, c->abort_flag.p, c->stream);
             ++launches;
-        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, nullptr, c->stream);
+        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->gram.p + self_ints, c->stream);
         c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 
@@ -371,8 +373,9 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_z = rp && c->rp_z.p ? c->rp_z.p + (size_t)it * M : nullptr;
         p.F = (int)F; p.fixed = c->d_fixed.p; p.fixperm = c->d_perm[slot].p + fo; p.fixG = c->fixG.p; p.alpha = c->alpha.p;
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
-        p.ll_part = c->ll.p; p.ll_bcast = p.ll_part + (size_t)c->nW * c->PS * 2; p.ll_delta = p.ll_bcast + (size_t)c->PS * 2;
-        p.ll_fin = p.ll_delta + ((size_t)2 * c->PS + 1) * 2;
+        p.ll_part = c->ll.p; p.ll_bcast = p.ll_part + 2 * (size_t)c->nW * c->PS * 2; p.ll_delta = p.ll_bcast + (3 * (size_t)c->PS + 1) * 2;
+        p.ll_fin = p.ll_delta + 2 * (size_t)c->PS * 2;
+        p.xgram = c->gram.p + self_ints;
         p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
         p.rank = c->win.rank; p.R = c->win.R;
         for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
@@ -411,7 +414,8 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     {
         int flag = 0;
         BRR_CUDA(cudaMemcpy(&flag, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
-        BRR_REQUIRE(flag == 0, BRR_E_CUDA, "sweep kernel watchdog fired (code " + std::to_string(flag) + "): grid hand-over timed out");
+        BRR_REQUIRE(flag == 0, BRR_E_CUDA, "in-kernel watchdog fired (code " + std::to_string(flag) + ": 2 bulk copy, 3 Gram sum over ranks, 10-16 sweep hand-overs: "
+                    "11 partial dots, 12 deltas, 13 flagged word, 14 fixed-effect totals, 15 block dots, 16 end-of-sweep sums)");
     }
     while (c->deliver_seq < c->snap_seq) {
         RowSnap &s = c->snaps[c->deliver_seq % ROW_RING];

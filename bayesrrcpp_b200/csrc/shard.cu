@@ -21,10 +21,10 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 void Window::layout(int PS, int nb, int B, int64_t Npad)
 {
     size_t o = 0;
-    off_xred = o; o = align_up(o + (size_t)2 * PS * R * 16, 256);
+    off_xred = o; o = align_up(o + (size_t)4 * PS * R * 16, 256);
     off_xfin = o; o = align_up(o + (size_t)R * 2 * 16, 256);
     off_ready = o; o = align_up(o + (size_t)R * 4, 256);
-    off_gram = o; if (R > 1) o = align_up(o + (size_t)nb * B * B * 4, 256);
+    off_gram = o; if (R > 1) o = align_up(o + (size_t)nb * B * (B + LOOKAHEAD) * 4, 256);
     off_eps = o; o = align_up(o + (size_t)Npad * 8, 256);
     bytes = o;
 }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant_
             uint32_t v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if ((int32_t)(v - q.epoch) >= 0) break;
-            if (clock64() - t0 > 20000000000LL || *reinterpret_cast<volatile int *>(q.abort_flag) != 0) { atomicExch(q.abort_flag, 3); s_ok = 0; break; }
+            if (clock64() - t0 > 20000000000LL || *reinterpret_cast<volatile int *>(q.abort_flag) != 0) { atomicCAS(q.abort_flag, 0, 3); s_ok = 0; break; }
         }
     }
     __syncthreads();

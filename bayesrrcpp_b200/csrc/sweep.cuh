@@ -29,6 +29,7 @@ struct SweepParams {
     // iteration inputs
     const int32_t *perm;          // M markers in visiting order
     const int32_t *gram;          // nb x B x B int32 (codes), rows/cols in visiting order
+    const int32_t *xgram;         // nb x LOOKAHEAD x B int32: products with the last LOOKAHEAD markers of the previous block
     const uint8_t *gtab;          // nb x table bytes: per-marker tables of this iteration (tables_kernel), sampler smem layout
     int64_t M; int nb;
     int64_t it;
@@ -57,15 +58,15 @@ struct SweepParams {
     double *alpha;                // F
     const double *tbl_fix_z;      // F or null
     // grid protocol
-    uint64_t *ll_part;            // PS x nW flagged-word slots (2 x u64 each), column-major: workers' partial dots; zeroed before launch
+    uint64_t *ll_part;            // 2 x PS x nW flagged-word slots (2 x u64 each; two phase parities): workers' partial dots; zeroed before launch
     // cross-rank exchange over peer memory (row-sharded chains; R == 1: this device's own window).  Never zeroed between
     // launches: flags are global phase numbers, monotone over the life of the chain.
     int rank, R;
-    uint64_t *xred[MAXR];         // every rank's window of column totals: [2 phase parities][PS][R] slots; this rank writes [.][.][rank]
+    uint64_t *xred[MAXR];         // every rank's window of column totals: [phase mod 4][PS][R] slots; this rank writes [.][.][rank]
     uint64_t *xfin[MAXR];         // every rank's window of end-of-sweep sums: [R][2] slots (sum eps, sum eps^2 over that rank's rows)
     uint32_t xphase0;             // global number of this launch's first phase
     uint64_t *ll_fin;             // nW x 2 slots: workers' sum eps, sum eps^2 -> sampler; zeroed before launch
-    uint64_t *ll_delta;           // PS slots: the sampler's per-marker deltas of the current block, streamed as they are decided
+    uint64_t *ll_delta;           // 2 x PS slots (two phase parities): the sampler's per-marker deltas, streamed as they are decided
     uint64_t *ll_bcast;           // (3 x PS + 1) slots: sampler -> workers delta, a*delta, d*delta (+ sentinel); zeroed before launch
     long long *prof;              // optional cycle accounting of the sampler CTA: wait, reduce, pass, publish, windows, full steps, blocks
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
