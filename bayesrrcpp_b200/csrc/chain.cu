@@ -508,6 +508,11 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
             if (bmin != c->B) choose_geometry(c.get(), bmin, cfg->workers);
             BRR_REQUIRE(c->B == bmin, BRR_E_SIZE, "ranks of a sharded chain cannot agree on a Gibbs block size");
         }
+        {   // every kernel of the iteration loop is loaded now, not on its first launch (common.cuh, preload_kernel)
+            const int kidx = c->kind == BRR_HORSESHOE ? 1 : 0;
+            preload_tables(kidx); preload_gram(c->B, c->gram_impl); preload_hyper(c->kind);
+            if (R > 1) preload_allsum();
+        }
         c->win.rank = c->comm.rank; c->win.R = R;
         c->win.layout(c->PS, c->nb, c->B, g->Npad);
         c->win.allocate();

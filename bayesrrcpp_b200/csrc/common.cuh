@@ -40,6 +40,15 @@ template <class F> int guarded(F &&body)
 // throws BRR_E_CUDA unless `device` exists and is compute capability 10.x; makes it current
 void require_device(int device);
 
+// Force the (lazily loaded) kernel into the context now.  Loading a kernel on its first launch can wait for the device to go
+// idle; a chain whose persistent sweep kernel is already spinning on a peer rank of the same device would then never see
+// that peer's launch.  Every kernel of the iteration loop is therefore loaded when the chain is created.
+template <class K> void preload_kernel(K *kernel)
+{
+    cudaFuncAttributes a;
+    BRR_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void *>(kernel)));
+}
+
 constexpr int ROW_PAD = 512;   // rows per column are padded to a multiple of this (codes 0): 128-byte column stride
 
 }  // namespace brr

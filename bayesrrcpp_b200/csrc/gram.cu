@@ -297,6 +297,20 @@ __global__ void __launch_bounds__(256) cross_bits_kernel(const uint8_t *__restri
 
 template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + GRAM_LA) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + GRAM_LA) * 4 + 64; }
 
+void preload_gram(int B, int impl)
+{
+    if (impl == 0) {
+        if (B == 32) preload_kernel(gram_tc_kernel<32, true>);
+        else if (B == 64) preload_kernel(gram_tc_kernel<64, true>);
+        else preload_kernel(gram_tc_kernel<128, true>);
+    } else {
+        if (B == 32) preload_kernel(gram_dp4a_kernel<32>);
+        else if (B == 64) preload_kernel(gram_dp4a_kernel<64>);
+        else preload_kernel(gram_dp4a_kernel<128>);
+        preload_kernel(cross_bits_kernel);
+    }
+}
+
 // launch on `stream`; G must hold nblocks * B * B int32
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream)
 {

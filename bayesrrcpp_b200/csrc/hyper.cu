@@ -173,6 +173,11 @@ void launch_hyper(const HyperParams &h, cudaStream_t stream)
     }
     BRR_CUDA(cudaGetLastError());
 }
+void preload_hyper(int kind)
+{
+    if (kind == BRR_HORSESHOE) { preload_kernel(hs_local_kernel); preload_kernel(hs_global_kernel); }
+    else preload_kernel(hyper_mixture_kernel);
+}
 int hyper_launch_count(int kind) { return kind == BRR_HORSESHOE ? 2 : 1; }
 
 }  // namespace brr

@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant_
 
 }  // namespace
 
+void preload_allsum() { preload_kernel(gram_allsum_kernel); }
+
 void launch_gram_allsum(const Window &w, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream)
 {
     AllSumParams q; memset(&q, 0, sizeof q);

@@ -83,6 +83,11 @@ void launch_sweep(int kind, int B, int TW, const SweepParams &p, size_t smem, cu
 // per-marker tables of the iteration described by `p` into gtab (nb x sweep_table_bytes); kind as for launch_sweep
 void launch_tables(int kind, int B, const SweepParams &p, uint8_t *gtab, cudaStream_t stream);
 size_t sweep_table_bytes(int kind, int B, int K, int G, int F);
+// load every kernel an iteration launches (see preload_kernel)
+void preload_tables(int kind);
+void preload_gram(int B, int impl);
+void preload_hyper(int kind);
+void preload_allsum();
 size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
