@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--markers", type=int, default=CFG["M"], help="markers M (default: BASELINE configs[1]; 500000 with --gpus 8 = configs[3])")
     ap.add_argument("--burn", type=int, default=CFG["chain_burn"], help="untimed chain burn-in iterations before the warm-up")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,7 +173,7 @@ def main():
             dist.all_reduce(t)
             a[:] = t.cpu().numpy()
     dev = local
-    N, M = CFG["N"], CFG["M"]                          # N: rows per GPU
+    N, M = CFG["N"], args.markers                      # N: rows per GPU
     geno = brr.Genotypes.synthetic(N, M, CFG["data_seed"], row0=rank * N, device=dev)
     if comm is not None:
         geno.shard_stats(comm)
@@ -253,9 +254,9 @@ def main():
     out = {"metric": "SNP-updates/sec", "value": value, "unit": "SNP-updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "block": geom["block"], "workers": geom["workers"],
+           "config": {"workload": WORKLOAD if M == CFG["M"] else WORKLOAD.replace("M=50000", "M=%d" % M).replace("BASELINE configs[1]", "BASELINE configs[3] shape" if M == 500000 else "non-default M"), "block": geom["block"], "workers": geom["workers"],
                       "rows_per_worker_max": geom["rows_per_worker_max"], "chain_burn_in_iterations": args.burn,
-                      "l2": "inputs larger than L2: 625 MB of packed genotypes are re-read every step",
+                      "l2": "inputs larger than L2: %d MB of packed genotypes per GPU are re-read every step" % (M * ((N + 3) // 4) // 1000000),
                       "parallelism": "1 GPU" if world == 1 else
                       "ONE chain over N_total=%d individuals, row-sharded over %d GPUs (%d rows each), chain replicated, per-block "
                       "exchange of partial dots over NVLink peer memory inside the sweep kernel" % (N * world, world, N),
