@@ -162,7 +162,7 @@ class Genotypes:
         order = np.ascontiguousarray(order, dtype=np.int32)
         nb = (len(order) + block - 1) // block
         G = np.zeros((nb, block, block), dtype=np.int32)
-        X = np.zeros((nb, 32, block), dtype=np.int32)
+        X = np.zeros((nb, lookahead(block), block), dtype=np.int32)
         ms = C.c_double()
         _check(lib().brr_gram_cross_blocks(self._h, order.ctypes.data_as(_ip), C.c_int64(len(order)), C.c_int(block), C.c_int(impl),
                                            G.ctypes.data_as(_ip), X.ctypes.data_as(_ip), C.byref(ms)))
@@ -349,6 +349,11 @@ def HorseshoeR(outputFile, seed, max_iterations, burn_in, thinning, X, Y, A, v0E
                                 C.c_int(thinning), _p(X), C.c_int64(X.shape[0]), C.c_int64(X.shape[1]), _p(Y),
                                 C.c_double(A), C.c_double(v0E), C.c_double(s02E), C.c_double(vL), C.c_double(vT),
                                 C.c_double(c2), C.c_double(vC), C.c_double(sC)))
+
+
+def lookahead(block):
+    """markers of a Gibbs block whose deltas reach the next block through the cross-Gram correction (csrc/common.cuh)"""
+    return 64 if block >= 64 else 32
 
 
 def draws_sample(seed, stream, it, idx0, n, kind, shape=1.0):

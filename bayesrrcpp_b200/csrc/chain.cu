@@ -255,7 +255,7 @@ void chain_init(brr_chain *c)
     c->fin.alloc(2); c->fin.zero();
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
-    c->gram.alloc((size_t)c->nb * c->B * (c->B + LOOKAHEAD));      // self tiles, then the look-ahead cross tiles
+    c->gram.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
@@ -350,7 +350,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         c->perm_used[slot] = true;
 
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
-        const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + LOOKAHEAD);
+        const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
         if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
             int32_t *part = c->win.gram(c->win.rank);
             launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->stream);

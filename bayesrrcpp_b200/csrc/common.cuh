@@ -49,6 +49,10 @@ template <class K> void preload_kernel(K *kernel)
     BRR_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void *>(kernel)));
 }
 
+// Look-ahead depth of the sweep for Gibbs blocks of B markers: the deltas of the last lookahead(B) markers of a block reach the
+// next block through the cross-Gram correction instead of through the workers' dots (sweep.cu, gram.cu).
+__host__ __device__ constexpr int lookahead(int B) { return B >= 64 ? 64 : 32; }
+
 constexpr int ROW_PAD = 512;   // rows per column are padded to a multiple of this (codes 0): 128-byte column stride
 
 }  // namespace brr

@@ -14,9 +14,9 @@ namespace brr {
 constexpr int GRAM_KC = 256;                       // rows (K) per operand tile (one commit group of MMAs)
 constexpr int GRAM_LDR = 1024;                     // rows per load stage: ONE 256-byte bulk copy per marker (bulk copies have a fixed
                                                    // issue cost of tens of cycles each; 128-byte copies left the kernel copy-issue bound)
-constexpr int GRAM_LA = 32;                        // look-ahead markers: the last GRAM_LA markers of the previous block (cross products)
+constexpr int GRAM_LA_MAX = 64;                    // look-ahead markers (lookahead(B) <= 64): the tail of the previous block (cross products)
 constexpr int GRAM_STAGE_ROW = GRAM_LDR / 4 + 16;  // bytes per staged packed column (padded: conflict-free 128-bit reads)
-constexpr int GRAM_TILE_BYTES = (128 + GRAM_LA) * GRAM_KC;   // int8 operand tile: up to 128 + 32 marker rows x KC
+constexpr int GRAM_TILE_BYTES = (128 + GRAM_LA_MAX) * GRAM_KC;   // int8 operand tile: up to 128 + 64 marker rows x KC
 constexpr int GRAM_SBO = (GRAM_KC / 16) * 128;     // byte stride between 8-marker groups
 constexpr int GRAM_LBO = 128;                      // byte stride between K-adjacent 8x16B core matrices
 
@@ -67,16 +67,17 @@ __device__ __forceinline__ uint4 expand16(uint32_t w)
     return r;
 }
 
-// CROSS: additionally X[blk][jl][k] = sum_n code[n, order[blk*B - 32 + jl]] * code[n, order[blk*B + k]] -- the products of the
-// block's markers with the last 32 markers of the previous block (the look-ahead correction of the sweep):
-// those 32 markers are 32 more rows of the B operand (N = B + 32 columns of the accumulator), the A operand is unchanged.
+// CROSS: additionally X[blk][jl][k] = sum_n code[n, order[blk*B - LA + jl]] * code[n, order[blk*B + k]], LA = lookahead(B) -- the
+// products of the block's markers with the last LA markers of the previous block (the look-ahead correction of the sweep,
+// DESIGN.md 3.1): those markers are LA more rows of the B operand (N = B + LA columns of the accumulator), A is unchanged.
 template <int B, bool CROSS>
 __global__ void __launch_bounds__(256, 1)
 gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G, int32_t *__restrict__ X)
 {
     static_assert(B == 32 || B == 64 || B == 128, "block size");
-    constexpr int R = CROSS ? B + GRAM_LA : B;              // marker rows of the operand tile
+    constexpr int LA = lookahead(B);
+    constexpr int R = CROSS ? B + LA : B;                   // marker rows of the operand tile
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *tile0 = smem;                                  // 2 x 64 KB operand tiles
     uint8_t *stage0 = smem + 2 * GRAM_TILE_BYTES;           // 2 x R x GRAM_STAGE_ROW staged packed columns
@@ -89,7 +90,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     uint64_t *full = bars, *freeb = bars + 2;
 
     if (tid < R) {
-        const int64_t o = tid < B ? blk * B + tid : blk * B - GRAM_LA + (tid - B);   // rows B.. : tail of the previous block
+        const int64_t o = tid < B ? blk * B + tid : blk * B - LA + (tid - B);   // rows B.. : tail of the previous block
         cols[tid] = (o >= 0 && o < n_order && (tid < B || blk > 0)) ? order[o] : -1;
     }
     // zero both operand tiles (rows of padding markers and rows >= R must read as 0) and both stages
@@ -123,7 +124,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     };
     if (nvalid == 0) {   // nothing to do but keep the protocol simple: write zeros
         for (int i = tid; i < B * B; i += 256) G[blk * B * B + i] = 0;
-        if (CROSS) for (int i = tid; i < GRAM_LA * B; i += 256) X[blk * GRAM_LA * B + i] = 0;
+        if (CROSS) for (int i = tid; i < LA * B; i += 256) X[blk * LA * B + i] = 0;
     } else {
         issue_loads(0);
         if (nloads > 1) issue_loads(1);
@@ -198,9 +199,11 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                     for (int q = 0; q < 8; ++q) dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
                 }
             }
-            if (CROSS) {   // accumulator columns B .. B + 31: products with the previous block's tail, stored [jl][k]
+            if (CROSS)     // accumulator columns B .. B + LA - 1: products with the previous block's tail, stored [jl][k]
+#pragma unroll
+            for (int x0 = 0; x0 < LA; x0 += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)B;
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(B + x0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -213,7 +216,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (row < B) {
 #pragma unroll
-                    for (int jl = 0; jl < 32; ++jl) X[(blk * GRAM_LA + jl) * B + row] = (int)v[jl];
+                    for (int jl = 0; jl < 32; ++jl) X[(blk * LA + x0 + jl) * B + row] = (int)v[jl];
                 }
             }
         }
@@ -278,9 +281,10 @@ __global__ void __launch_bounds__(256) cross_bits_kernel(const uint8_t *__restri
 {
     const int64_t blk = blockIdx.x;
     const int64_t nwords = Npad / 16;
-    for (int pair = threadIdx.x; pair < GRAM_LA * B; pair += blockDim.x) {
+    const int LA = lookahead(B);
+    for (int pair = threadIdx.x; pair < LA * B; pair += blockDim.x) {
         const int jl = pair / B, k = pair % B;
-        const int64_t oj = blk * B - GRAM_LA + jl, ok = blk * B + k;
+        const int64_t oj = blk * B - LA + jl, ok = blk * B + k;
         int32_t acc = 0;
         if (blk > 0 && oj >= 0 && ok < n_order && order[oj] >= 0 && order[ok] >= 0) {
             const uint32_t *a = reinterpret_cast<const uint32_t *>(packed + (int64_t)order[oj] * stride);
@@ -291,11 +295,11 @@ __global__ void __launch_bounds__(256) cross_bits_kernel(const uint8_t *__restri
                 acc += __popc(xl & yl) + 2 * (__popc(xl & yh) + __popc(xh & yl)) + 4 * __popc(xh & yh);
             }
         }
-        X[(blk * GRAM_LA + jl) * B + k] = acc;
+        X[(blk * LA + jl) * B + k] = acc;
     }
 }
 
-template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + GRAM_LA) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + GRAM_LA) * 4 + 64; }
+template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + lookahead(B)) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + lookahead(B)) * 4 + 64; }
 
 void preload_gram(int B, int impl)
 {
@@ -359,7 +363,7 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
         try {
             BRR_CUDA(cudaMalloc(&d_order, n_order * 4));
             BRR_CUDA(cudaMalloc(&d_G, (size_t)nb * block * block * 4));
-            if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * GRAM_LA * block * 4));
+            if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * lookahead(block) * block * 4));
             BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
             launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0);   // warm-up (module load, attribute)
@@ -369,7 +373,7 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
             BRR_CUDA(cudaEventSynchronize(e1));
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;
             BRR_CUDA(cudaMemcpy(G_out, d_G, (size_t)nb * block * block * 4, cudaMemcpyDeviceToHost));
-            if (X_out) BRR_CUDA(cudaMemcpy(X_out, d_X, (size_t)nb * GRAM_LA * block * 4, cudaMemcpyDeviceToHost));
+            if (X_out) BRR_CUDA(cudaMemcpy(X_out, d_X, (size_t)nb * lookahead(block) * block * 4, cudaMemcpyDeviceToHost));
         } catch (...) { cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
         cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); cudaEventDestroy(e0); cudaEventDestroy(e1);
     });

@@ -24,7 +24,7 @@ void Window::layout(int PS, int nb, int B, int64_t Npad)
     off_xred = o; o = align_up(o + (size_t)4 * PS * R * 16, 256);
     off_xfin = o; o = align_up(o + (size_t)R * 2 * 16, 256);
     off_ready = o; o = align_up(o + (size_t)R * 4, 256);
-    off_gram = o; if (R > 1) o = align_up(o + (size_t)nb * B * (B + LOOKAHEAD) * 4, 256);
+    off_gram = o; if (R > 1) o = align_up(o + (size_t)nb * B * (B + lookahead(B)) * 4, 256);
     off_eps = o; o = align_up(o + (size_t)Npad * 8, 256);
     bytes = o;
 }

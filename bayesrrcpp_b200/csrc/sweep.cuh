@@ -29,7 +29,7 @@ struct SweepParams {
     // iteration inputs
     const int32_t *perm;          // M markers in visiting order
     const int32_t *gram;          // nb x B x B int32 (codes), rows/cols in visiting order
-    const int32_t *xgram;         // nb x LOOKAHEAD x B int32: products with the last LOOKAHEAD markers of the previous block
+    const int32_t *xgram;         // nb x lookahead(B) x B int32: products with the last lookahead(B) markers of the previous block
     const uint8_t *gtab;          // nb x table bytes: per-marker tables of this iteration (tables_kernel), sampler smem layout
     int64_t M; int nb;
     int64_t it;
@@ -91,8 +91,7 @@ void preload_allsum();
 size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
-// d_G: nb x B x B self products; d_X (nullable): nb x LOOKAHEAD x B products with the last LOOKAHEAD markers of the previous block
+// d_G: nb x B x B self products; d_X (nullable): nb x lookahead(B) x B products with the last lookahead(B) markers of the previous block
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream);
-constexpr int LOOKAHEAD = 32;     // markers of a block whose deltas reach the next block through the cross-Gram correction instead of the dots
 
 }  // namespace brr

@@ -197,8 +197,9 @@ int brr_comm_selftest(const brr_comm *comm, double *buf, int64_t n, int64_t toke
  * gram: G[b][i][j] = sum_n code[n, order[b*B+i]] * code[n, order[b*B+j]]  (int32, nb x B x B; order index -1 = padding) */
 int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
                     int32_t *G_out, double *ms);
-/* same, plus X[b][jl][k] = sum_n code[n, order[b*B - 32 + jl]] * code[n, order[b*B + k]] (int32, nb x 32 x B; block 0: zeros):
- * the products with the last 32 markers of the previous block that the sweep's look-ahead correction uses (X_out may be NULL) */
+/* same, plus X[b][jl][k] = sum_n code[n, order[b*B - LA + jl]] * code[n, order[b*B + k]] (int32, nb x LA x B; block 0: zeros),
+ * LA = 64 for blocks of 64 or 128 markers, 32 for blocks of 32: the products with the last LA markers of the previous block
+ * that the sweep's look-ahead correction uses (X_out may be NULL) */
 int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
                           int32_t *G_out, int32_t *X_out, double *ms);
 /* r[j] = sum_n x[n, j] * eps[n] for every marker (host eps N -> host r M), the streaming X^T eps kernel */

@@ -83,7 +83,8 @@ def test_gram_tensor_core_is_bit_exact(po, brr, block):
 
 @pytest.mark.parametrize("block", [128, 64, 32])
 def test_gram_cross_products_with_previous_block_tail(po, brr, block):
-    """look-ahead tiles: X[b][jl][k] = codes[:, order[b*B-32+jl]] . codes[:, order[b*B+k]], tensor cores == bit-sliced CUDA cores == numpy"""
+    """look-ahead tiles: X[b][jl][k] = codes[:, order[b*B-LA+jl]] . codes[:, order[b*B+k]], tensor cores == bit-sliced CUDA cores == numpy"""
+    LA = brr.lookahead(block)
     d = po.synth(1100, 300, seed=15)
     g = brr.Genotypes.from_dense(d["X"])
     codes = g.unpack().astype(np.int64)
@@ -94,9 +95,9 @@ def test_gram_cross_products_with_previous_block_tail(po, brr, block):
     nb = (g.M + block - 1) // block
     assert not X_tc[0].any()
     for b in range(1, nb):
-        prev = order[b * block - 32:b * block]
+        prev = order[b * block - LA:b * block]
         cur = order[b * block:(b + 1) * block]
-        want = np.zeros((32, block), dtype=np.int64)
+        want = np.zeros((LA, block), dtype=np.int64)
         want[:, :len(cur)] = codes[:, prev].T @ codes[:, cur]
         assert np.array_equal(X_tc[b], want), "block %d" % b
 
