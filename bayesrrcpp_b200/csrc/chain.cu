@@ -129,7 +129,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     int dev = 0, sms = 0;
     BRR_CUDA(cudaGetDevice(&dev));
     BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int kidx = c->kind == BRR_HORSESHOE ? 1 : (c->K == 3 || c->K == 4) ? 2 : 0;   // sweep-kernel variant
+    const int kidx = c->kind == BRR_HORSESHOE ? 1 : c->K == 4 ? 2 : c->K == 3 ? 3 : 0;   // sweep-kernel variant
     BRR_REQUIRE(c->kind == BRR_HORSESHOE || (c->K >= 2 && c->K <= KMAX), BRR_E_SIZE,
                 "number of mixture components must be in [2, " + std::to_string(KMAX) + "]");
     const int64_t units = (c->N + 63) / 64;
@@ -326,7 +326,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     const bool sharded = c->win.R > 1;
     if (sharded) { double token = 1.0; comm_allreduce(c->comm, &token, 1); }    // ranks enter the launch sequence together
     const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
-    const int kk = c->kind == BRR_HORSESHOE ? 1 : (K == 3 || K == 4) ? 2 : 0;   // sweep-kernel variant
+    const int kk = c->kind == BRR_HORSESHOE ? 1 : K == 4 ? 2 : K == 3 ? 3 : 0;   // sweep-kernel variant
     int64_t launches = 0;
     c->prof.zero(c->stream);
     while (c->kev.size() < (size_t)4 * n_iter) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }

@@ -217,7 +217,7 @@ def test_v2_uninitialised_pi_quirk_and_fall_through(po, brr):
     _compare_v2(o, rows, N, M)
 
 
-@pytest.mark.parametrize("cva", [[1e-3], [1e-5, 1e-4, 1e-3, 1e-2, 1e-1], [1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 0.5]])
+@pytest.mark.parametrize("cva", [[1e-3], [1e-3, 1e-2], [1e-5, 1e-4, 1e-3, 1e-2, 1e-1], [1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 0.5]])
 def test_v2_other_component_counts(po, brr, cva):
     N, M, T = 700, 200, 15
     d = po.synth(N, M, seed=23)
