@@ -66,7 +66,15 @@ struct brr_chain {
     DevBuf<double> beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
     DevBuf<double> fin;
     DevBuf<uint64_t> ll;                     // flagged-word hand-over buffers inside the device: [part nW*PS | bcast PS | delta 2*PS+1 | fin 2*nW] slots
-    DevBuf<int32_t> d_gAssign, unit0, gram;
+    DevBuf<int32_t> d_gAssign, unit0, gram[2];      // block Gram + cross tiles of iterations it (it & 1) and it + 1
+    // Gram pipeline: the Gram of iteration it + 1 depends only on that iteration's marker order, so it runs on its own stream,
+    // on the SMs the sweep kernel of iteration it leaves free (a persistent grid of gram_ctas CTAs)
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_gram0[2] = {}, ev_gram1[2] = {}, ev_sweep_done[2] = {};
+    bool sweep_recorded[2] = {false, false};
+    int64_t prepared_upto = -1;                      // marker order + Gram are in place for iterations <= this
+    int gram_ctas = 0;
+    std::vector<int64_t> gram_timed;                 // iterations whose Gram events belong to the current brr_chain_run
     DevBuf<IterScalars> sc;
     DevBuf<int> abort_flag;
     DevBuf<long long> prof;
@@ -104,6 +112,8 @@ struct brr_chain {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
+        if (gstream) cudaStreamDestroy(gstream);
+        for (int i = 0; i < 2; ++i) { if (ev_gram0[i]) cudaEventDestroy(ev_gram0[i]); if (ev_gram1[i]) cudaEventDestroy(ev_gram1[i]); if (ev_sweep_done[i]) cudaEventDestroy(ev_sweep_done[i]); }
         win.release();
     }
 };
@@ -135,7 +145,9 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     const int64_t units = (c->N + 63) / 64;
     int B = want_block ? want_block : 128;
     BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
-    int nW = want_workers > 0 ? want_workers : sms - 1;
+    // SMs set aside for the Gram kernel of the next iteration, which runs beside the sweep (none when the caller fixes the workers)
+    const int gram_sms = want_workers > 0 ? 0 : (sms >= 64 ? (sms * 3 + 8) / 16 : 0);
+    int nW = want_workers > 0 ? want_workers : sms - 1 - gram_sms;
     nW = (int)std::max<int64_t>(1, std::min<int64_t>(nW, units));
     while (true) {
         const int64_t maxu = (units + nW - 1) / nW;
@@ -153,6 +165,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         BRR_REQUIRE(cores >= 2, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
         if (nW + 1 > cores) { nW = cores - 1; continue; }
         c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->smem = smem;
+        c->gram_ctas = std::max(1, sms - (nW + 1));
         break;
     }
     c->PS = (int)std::max<int64_t>(c->B, c->F);
@@ -255,7 +268,7 @@ void chain_init(brr_chain *c)
     c->fin.alloc(2); c->fin.zero();
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
-    c->gram.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
+    for (auto &gb : c->gram) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
@@ -331,32 +344,48 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     c->prof.zero(c->stream);
     while (c->kev.size() < (size_t)4 * n_iter) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
     BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
+    const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
+    const size_t fo = (size_t)c->nb * c->B;
+    c->gram_timed.clear();
+    // Marker order (host shuffle, reference :182) + block Gram of iteration j, on the Gram stream.  Called once per iteration,
+    // in order, one iteration ahead of the sweep.
+    auto prepare = [&](int64_t j) {
+        const bool rp = c->replay;
+        const int slot = (int)(j % PERM_RING), gb = (int)(j & 1);
+        if (c->perm_used[slot]) BRR_CUDA(cudaEventSynchronize(c->perm_free[slot]));
+        int32_t *hp = c->h_perm[slot].p;
+        if (rp) memcpy(hp, &c->rp_perm[(size_t)j * M], (size_t)M * 4);
+        else { shuffle_host(c->key, S_PERM, j, c->markerI.data(), M); memcpy(hp, c->markerI.data(), (size_t)M * 4); }   // :182
+        if (F > 0) {
+            if (rp) memcpy(hp + fo, &c->rp_fixperm[(size_t)j * F], (size_t)F * 4);
+            else { shuffle_host(c->key, S_FIXPERM, j, c->fixedI.data(), F); memcpy(hp + fo, c->fixedI.data(), (size_t)F * 4); }   // Groups:216
+        }
+        // the Gram buffer j & 1 was last read by the sweep of iteration j - 2
+        if (c->sweep_recorded[gb]) BRR_CUDA(cudaStreamWaitEvent(c->gstream, c->ev_sweep_done[gb], 0));
+        BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p, hp, (size_t)(M) * 4, cudaMemcpyHostToDevice, c->gstream));
+        if (F > 0) BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p + fo, hp + fo, (size_t)F * 4, cudaMemcpyHostToDevice, c->gstream));
+        c->perm_used[slot] = true;
+        BRR_CUDA(cudaEventRecord(c->ev_gram0[gb], c->gstream));
+        if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
+            int32_t *part = c->win.gram(c->win.rank, gb);
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->gstream, c->gram_ctas);
+            launch_gram_allsum(c->win, gb, (uint32_t)j + 1u, c->gram[gb].p, all_ints, c->abort_flag.p, c->gstream, c->gram_ctas);
+            ++launches;
+        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram[gb].p, c->gram[gb].p + self_ints, c->gstream, c->gram_ctas);
+        BRR_CUDA(cudaEventRecord(c->ev_gram1[gb], c->gstream));
+        c->prepared_upto = j;
+        ++launches;
+    };
+    auto can_prepare = [&](int64_t j) { return !c->replay || j < c->rp_iters; };
     for (int n = 0; n < n_iter; ++n) {
         const int64_t it = c->it;
         const bool rp = c->replay;
         if (rp) BRR_REQUIRE(it < c->rp_iters, BRR_E_ARG, "replay tables exhausted");
-        const int slot = (int)(it % PERM_RING);
-        if (c->perm_used[slot]) BRR_CUDA(cudaEventSynchronize(c->perm_free[slot]));
-        int32_t *hp = c->h_perm[slot].p;
-        if (rp) memcpy(hp, &c->rp_perm[(size_t)it * M], (size_t)M * 4);
-        else { shuffle_host(c->key, S_PERM, it, c->markerI.data(), M); memcpy(hp, c->markerI.data(), (size_t)M * 4); }   // :182
-        const size_t fo = (size_t)c->nb * c->B;
-        if (F > 0) {
-            if (rp) memcpy(hp + fo, &c->rp_fixperm[(size_t)it * F], (size_t)F * 4);
-            else { shuffle_host(c->key, S_FIXPERM, it, c->fixedI.data(), F); memcpy(hp + fo, c->fixedI.data(), (size_t)F * 4); }   // Groups:216
-        }
-        BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p, hp, (size_t)(M) * 4, cudaMemcpyHostToDevice, c->stream));
-        if (F > 0) BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p + fo, hp + fo, (size_t)F * 4, cudaMemcpyHostToDevice, c->stream));
-        c->perm_used[slot] = true;
-
+        const int slot = (int)(it % PERM_RING), gb = (int)(it & 1);
+        if (c->prepared_upto < it) prepare(it);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
-        const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
-        if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
-            int32_t *part = c->win.gram(c->win.rank);
-            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->stream);
-            launch_gram_allsum(c->win, (uint32_t)it + 1u, c->gram.p, all_ints, c->abort_flag.p, c->stream);
-            ++launches;
-        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram.p, c->gram.p + self_ints, c->stream);
+        BRR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gram1[gb], 0));
+        c->gram_timed.push_back(it);
         c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 
@@ -364,7 +393,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         const brr_geno *g = c->g;
         p.packed = g->d_packed; p.stride = g->stride; p.N = g->N;
         p.colA = g->d_a; p.colD = g->d_d; p.colS = g->d_S; p.colXsq = g->d_xsq; p.colCsum = g->d_csum; p.n_total = g->n_total;
-        p.perm = c->d_perm[slot].p; p.gram = c->gram.p; p.M = M; p.nb = c->nb; p.it = it;
+        p.perm = c->d_perm[slot].p; p.gram = c->gram[gb].p; p.M = M; p.nb = c->nb; p.it = it;
         p.eps = c->d_eps; p.beta = c->beta.p; p.comp = c->comp.p; p.sc = c->sc.p;
         p.K = K; p.G = G; p.gAssign = c->d_gAssign.p; p.cva = c->d_cva.p; p.sigmaG = c->sigmaG.p; p.pi = c->pi.p;
         p.vcount = c->vcount.p; p.betaAcum = c->betaAcum.p; p.lambda = c->lambda.p;
@@ -375,7 +404,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         p.tbl_fix_z = rp && F > 0 && c->rp_fixz.p ? c->rp_fixz.p + (size_t)it * F : nullptr;
         p.ll_part = c->ll.p; p.ll_bcast = p.ll_part + 2 * (size_t)c->nW * c->PS * 2; p.ll_delta = p.ll_bcast + (3 * (size_t)c->PS + 1) * 2;
         p.ll_fin = p.ll_delta + 2 * (size_t)c->PS * 2;
-        p.xgram = c->gram.p + self_ints;
+        p.xgram = c->gram[gb].p + self_ints;
         p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
         p.rank = c->win.rank; p.R = c->win.R;
         for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
@@ -386,6 +415,10 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
         BRR_CUDA(cudaEventRecord(c->perm_free[slot], c->stream));
+        BRR_CUDA(cudaEventRecord(c->ev_sweep_done[gb], c->stream));
+        c->sweep_recorded[gb] = true;
+        // next iteration's marker order and Gram: beside this sweep, on the SMs it leaves free
+        if (c->prepared_upto < it + 1 && can_prepare(it + 1)) prepare(it + 1);
 
         HyperParams h; memset(&h, 0, sizeof h);
         h.kind = c->kind; h.it = it; h.n_total = g->n_total; h.M = M; h.K = K; h.G = G; h.F = F;
@@ -402,7 +435,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         h.tbl_hs_nu_next = next_in && c->rp_nu.p ? c->rp_nu.p + (size_t)(it + 1) * M : nullptr;
         launch_hyper(h, c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 3], c->stream));
-        launches += 3 + hyper_launch_count(c->kind);
+        launches += 2 + hyper_launch_count(c->kind);
 
         if (emit_all || (it >= c->burn_in && it % c->thinning == 0))                     // :257-259
             snapshot_row(c, it, rows, max_rows, n_rows);
@@ -410,6 +443,7 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     }
     BRR_CUDA(cudaEventRecord(c->ev1, c->stream));
     BRR_CUDA(cudaStreamSynchronize(c->stream));
+    BRR_CUDA(cudaStreamSynchronize(c->gstream));
     if (sharded) { double token = 1.0; comm_allreduce(c->comm, &token, 1); }    // no rank leaves while a peer may still be copying its residuals
     {
         int flag = 0;
@@ -426,10 +460,21 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     c->last_ms = ms; c->last_launches = launches;
     c->last_kernel_ms[0] = c->last_kernel_ms[1] = c->last_kernel_ms[2] = 0;
     for (int n = 0; n < n_iter; ++n)
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 1; k < 3; ++k) {
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, c->kev[4 * n + k], c->kev[4 * n + k + 1]));
             c->last_kernel_ms[k] += t;
         }
+    // the Gram kernel runs beside the sweep of the previous iteration: its own duration is only known for the two most recent
+    // preparations (their events are still in place); scale to the run
+    {
+        double sum = 0; int cnt = 0;
+        for (int gb = 0; gb < 2; ++gb) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, c->ev_gram0[gb], c->ev_gram1[gb]) == cudaSuccess) { sum += t; ++cnt; }
+        }
+        (void)cudaGetLastError();
+        c->last_kernel_ms[0] = cnt ? sum / cnt * n_iter : 0.0;
+    }
 }
 
 void check_iters(int max_iterations, int burn_in, int thinning)
@@ -522,6 +567,11 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         if (R > 1) BRR_REQUIRE((double)c->N_total == g->n_total, BRR_E_ARG,
                                "the genotype store of a sharded chain needs brr_geno_shard_stats first (its statistics must cover all ranks' rows)");
         BRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        BRR_CUDA(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            BRR_CUDA(cudaEventCreate(&c->ev_gram0[i])); BRR_CUDA(cudaEventCreate(&c->ev_gram1[i]));
+            BRR_CUDA(cudaEventCreateWithFlags(&c->ev_sweep_done[i], cudaEventDisableTiming));
+        }
         BRR_CUDA(cudaEventCreate(&c->ev0)); BRR_CUDA(cudaEventCreate(&c->ev1));
         *out = c.release();
     });

@@ -86,9 +86,21 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     int32_t *cols = reinterpret_cast<int32_t *>(tmem_slot + 2);                        // R marker ids
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int64_t blk = blockIdx.x;
     uint64_t *full = bars, *freeb = bars + 2;
+    const int64_t nblocks = (n_order + B - 1) / B;
 
+    if (warp == 0) {   // TMEM: 128 lanes x 256 int32 columns (B + lookahead used)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    // Persistent over blocks: the grid may be smaller than the number of blocks -- the chain runs this kernel on the SMs the
+    // sweep kernel of the previous iteration leaves free (chain.cu), a grid of that many CTAs.
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     if (tid < R) {
         const int64_t o = tid < B ? blk * B + tid : blk * B - LA + (tid - B);   // rows B.. : tail of the previous block
         cols[tid] = (o >= 0 && o < n_order && (tid < B || blk > 0)) ? order[o] : -1;
@@ -97,18 +109,13 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     for (int i = tid; i < (2 * GRAM_TILE_BYTES + 2 * R * GRAM_STAGE_ROW) / 16; i += 256)
         reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
+        if (blk != (int64_t)blockIdx.x)
+            for (int i = 0; i < 4; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
         mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&freeb[0], 1); mbar_init(&freeb[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: 128 lanes x 256 int32 columns (B + 32 used)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
 
     const int nloads = (int)((Npad + GRAM_LDR - 1) / GRAM_LDR);
     int nvalid = 0;
@@ -222,7 +229,9 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();            // the accumulator has been read out and every thread is done with this block's barriers
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
@@ -316,7 +325,8 @@ void preload_gram(int B, int impl)
 }
 
 // launch on `stream`; G must hold nblocks * B * B int32
-void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream)
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
+                 int max_ctas)
 {
 
     const int64_t nb = (n_order + B - 1) / B;
@@ -331,8 +341,9 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
                 BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
                 attr_set = true;                                                                                            \
             }                                                                                                               \
-            if (d_X) gram_tc_kernel<BB, true><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X); \
-            else gram_tc_kernel<BB, false><<<(unsigned)nb, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr); \
+            const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);                                \
+            if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X); \
+            else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr); \
         } else {                                                                                                            \
             gram_dp4a_kernel<BB><<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G);      \
         }                                                                                                                   \
@@ -366,9 +377,9 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
             if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * lookahead(block) * block * 4));
             BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
-            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0);   // warm-up (module load, attribute)
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0);   // warm-up (module load, attribute)
             BRR_CUDA(cudaEventRecord(e0));
-            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0);
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0);
             BRR_CUDA(cudaEventRecord(e1));
             BRR_CUDA(cudaEventSynchronize(e1));
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;

@@ -24,7 +24,8 @@ void Window::layout(int PS, int nb, int B, int64_t Npad)
     off_xred = o; o = align_up(o + (size_t)4 * PS * R * 16, 256);
     off_xfin = o; o = align_up(o + (size_t)R * 2 * 16, 256);
     off_ready = o; o = align_up(o + (size_t)R * 4, 256);
-    off_gram = o; if (R > 1) o = align_up(o + (size_t)nb * B * (B + lookahead(B)) * 4, 256);
+    gram_bytes = align_up((size_t)nb * B * (B + lookahead(B)) * 4, 256);
+    off_gram = o; if (R > 1) o = o + 2 * gram_bytes;
     off_eps = o; o = align_up(o + (size_t)Npad * 8, 256);
     bytes = o;
 }
@@ -128,12 +129,12 @@ __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant_
 
 void preload_allsum() { preload_kernel(gram_allsum_kernel); }
 
-void launch_gram_allsum(const Window &w, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream)
+void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream, int max_ctas)
 {
     AllSumParams q; memset(&q, 0, sizeof q);
     q.rank = w.rank; q.R = w.R; q.epoch = epoch; q.sum = d_sum; q.n4 = n_int32 / 4; q.abort_flag = abort_flag;
-    for (int r = 0; r < w.R; ++r) { q.ready[r] = w.ready(r); q.part[r] = w.gram(r); }
-    const unsigned blocks = (unsigned)std::min<size_t>((q.n4 + 255) / 256, 148 * 8);
+    for (int r = 0; r < w.R; ++r) { q.ready[r] = w.ready(r); q.part[r] = w.gram(r, buf); }
+    const unsigned blocks = (unsigned)std::min<size_t>((q.n4 + 255) / 256, (size_t)(max_ctas > 0 ? max_ctas : 148) * 8);
     gram_allsum_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(q);
     BRR_CUDA(cudaGetLastError());
 }

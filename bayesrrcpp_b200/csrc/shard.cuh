@@ -35,13 +35,14 @@ struct Window {
     uint64_t *xred(int r) const { return reinterpret_cast<uint64_t *>(peer[r] + off_xred); }
     uint64_t *xfin(int r) const { return reinterpret_cast<uint64_t *>(peer[r] + off_xfin); }
     uint32_t *ready(int r) const { return reinterpret_cast<uint32_t *>(peer[r] + off_ready); }
-    int32_t *gram(int r) const { return reinterpret_cast<int32_t *>(peer[r] + off_gram); }
+    size_t gram_bytes = 0;           // one partial-Gram buffer (two alternate: iteration parity)
+    int32_t *gram(int r, int buf) const { return reinterpret_cast<int32_t *>(peer[r] + off_gram + (size_t)buf * gram_bytes); }
     double *eps(int r) const { return reinterpret_cast<double *>(peer[r] + off_eps); }
 };
 
 // G_sum = sum over ranks of their partial block Grams (exact int32), every rank reading its peers' partials over NVLink.
 // Signals "my partial of iteration `epoch - 1` is complete" to every peer first, then waits for theirs.
-void launch_gram_allsum(const Window &w, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream);
+void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream, int max_ctas);
 
 void comm_check(int rc, const char *what);
 void comm_allreduce(const brr_comm &comm, double *buf, int64_t n);

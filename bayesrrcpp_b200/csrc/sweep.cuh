@@ -92,6 +92,8 @@ size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_by
 int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
 // d_G: nb x B x B self products; d_X (nullable): nb x lookahead(B) x B products with the last lookahead(B) markers of the previous block
-void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream);
+// max_ctas > 0: persistent grid of at most that many CTAs (the tensor-core kernel loops over the blocks)
+void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
+                 int max_ctas = 0);
 
 }  // namespace brr

@@ -1,6 +1,11 @@
 import os
 import sys
 
+# Ranks of a sharded chain run as threads on ONE device in tests/test_sharded.py: their persistent kernels wait for each other, so
+# every stream involved needs its own hardware queue (the default of 8 connections lets two of them share one).  Must be set
+# before CUDA initialises; irrelevant for one rank per GPU.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
