@@ -214,15 +214,20 @@ def main():
         g2 = brr.Genotypes.from_packed(codes, N, mean=st["mean"], sd=st["sd"], device=dev)    # H2D of the packed matrix
         if comm is not None:
             g2.shard_stats(comm)
+        t1 = time.perf_counter()
         c2 = brr.Chain(g2, brr.V2, args.steps, burn_in=1, thinning=thin, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"],
                        block=args.block, comm=comm, **CFG["hyp"])
         if rank == 0:
             c2.open_output(tmp.name)
+        t2 = time.perf_counter()
         kept = c2.run_discard(args.steps)                              # perm H2D per step, kept rows D2H + CSV writer
+        t3 = time.perf_counter()
         if rank == 0:
             c2.close_output()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
+        e2e_split = {"genotypes_h2d_ms": 1e3 * (t1 - t0), "chain_create_ms": 1e3 * (t2 - t1), "iterations_ms": 1e3 * (t3 - t2),
+                     "writer_drain_ms": 1e3 * (time.perf_counter() - t3)}
         te = torch.tensor([dt], dtype=torch.float64, device="cuda:%d" % dev)
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -231,6 +236,7 @@ def main():
         e2e = {"value": world * M * args.steps / dt, "unit": "SNP-updates/s",
                "h2d_bytes_per_step": int(codes.nbytes / args.steps + 4 * M + 8 * N / args.steps),
                "d2h_bytes_per_step": int(row_bytes * kept / args.steps),
+               "split_ms_rank0": e2e_split,
                "note": "brr_geno_from_packed(host codes) + brr_chain_create + %d iterations with CSV rows every %d; wall clock" % (args.steps, thin)}
         c2.close(); g2.close()
         os.unlink(tmp.name)
@@ -243,7 +249,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = None                                  # DRAM bytes of one sweep launch from the committed ncu --set full capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v3.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v5.json")) as f:
             k = [v for n, v in json.load(f).items() if "sweep_kernel" in n][0]
             traffic = int(1e6 * (float(k["dram__bytes_read.sum"]["value"]) + float(k["dram__bytes_write.sum"]["value"])))
     except Exception:
