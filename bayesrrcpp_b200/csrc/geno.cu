@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace brr {
 
@@ -347,6 +348,47 @@ static void stats_from_codes(brr_geno *g, const double *mean, const double *sd)
     cudaFree(d_bad); cudaFree(d_mean); cudaFree(d_sd);
 }
 
+// Host (pageable) columns -> device columns with the padded stride.  cudaMemcpy2D from pageable memory moves ~1.4 GB/s here;
+// instead the columns are re-strided by a few host threads into two pinned staging buffers whose 1-D copies overlap the next
+// chunk's staging.
+static void upload_columns(uint8_t *d_dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, size_t ncols)
+{
+    const size_t chunk_bytes = (size_t)16 << 20;
+    const size_t cols_per = std::max<size_t>(1, chunk_bytes / dpitch);
+    uint8_t *buf[2] = { nullptr, nullptr }; cudaEvent_t ev[2] = { nullptr, nullptr }; cudaStream_t st = nullptr;
+    try {
+        for (int i = 0; i < 2; ++i) {
+            BRR_CUDA(cudaMallocHost(&buf[i], std::min(cols_per, ncols) * dpitch));
+            BRR_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        BRR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        int i = 0; bool used[2] = { false, false };
+        for (size_t c0 = 0; c0 < ncols; c0 += cols_per, i ^= 1) {
+            const size_t n = std::min(cols_per, ncols - c0);
+            if (used[i]) BRR_CUDA(cudaEventSynchronize(ev[i]));
+            const int nthreads = 4;
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthreads; ++t)
+                th.emplace_back([=] {
+                    const size_t a = n * t / nthreads, b = n * (t + 1) / nthreads;
+                    if (spitch == dpitch) { if (b > a) memcpy(buf[i] + a * dpitch, src + (c0 + a) * spitch, (b - a) * dpitch - (dpitch - width)); }
+                    else for (size_t c = a; c < b; ++c) memcpy(buf[i] + c * dpitch, src + (c0 + c) * spitch, width);
+                });
+            for (auto &t : th) t.join();
+            BRR_CUDA(cudaMemcpyAsync(d_dst + c0 * dpitch, buf[i], n * dpitch - (dpitch - width), cudaMemcpyHostToDevice, st));
+            BRR_CUDA(cudaEventRecord(ev[i], st));
+            used[i] = true;
+        }
+        BRR_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+        if (st) cudaStreamDestroy(st);
+        throw;
+    }
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); }
+    cudaStreamDestroy(st);
+}
+
 extern "C" int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_bytes, int64_t N, int64_t M,
                                     const double *mean, const double *sd, int device, brr_geno **out)
 {
@@ -356,8 +398,7 @@ extern "C" int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_by
         BRR_REQUIRE(col_stride_bytes >= width, BRR_E_ARG, "col_stride_bytes smaller than ceil(N/4)");
         brr_geno *g = geno_alloc(N, M, device);
         try {
-            BRR_CUDA(cudaMemcpy2D(g->d_packed, (size_t)g->stride, packed, (size_t)col_stride_bytes, (size_t)width, (size_t)M,
-                                  cudaMemcpyHostToDevice));
+            upload_columns(g->d_packed, (size_t)g->stride, packed, (size_t)col_stride_bytes, (size_t)width, (size_t)M);
             stats_from_codes(g, mean, sd);
         } catch (...) { brr_geno_free(g); throw; }
         *out = g;

@@ -9,6 +9,8 @@
 #include "writer.h"
 #include <cstdio>
 #include <cstring>
+#include <charconv>
+#include <cmath>
 
 namespace brr {
 
@@ -42,9 +44,9 @@ bool RowQueue::try_dequeue(std::vector<double> &row)
 
 static void put_indexed(std::string &s, const char *name, long i, const char *tail)
 {
-    char t[64];
-    snprintf(t, sizeof t, "%s[%ld]%s", name, i, tail);
-    s += t;
+    char t[24];
+    const auto r = std::to_chars(t, t + sizeof t, i);
+    s += name; s.push_back('['); s.append(t, (size_t)(r.ptr - t)); s.push_back(']'); s += tail;
 }
 
 // Header text per sampler: src/BayesRv2.cpp:16-37, src/BayesRv2Groups.cpp:25-54, src/HorseshoeR.cpp:279-291 (trailing comma).
@@ -78,15 +80,32 @@ std::string sample_header(int kind, int64_t N, int64_t M, int G, int64_t F)
     return s;
 }
 
+// "%g" of every value (ostream precision 6, reference src/BayesRv2.cpp:72), joined by ", ".  Rows are long (2M + 4 + N numbers)
+// and mostly zeros and small integers, so those take a short cut; everything else goes through std::to_chars, which is
+// specified to produce what printf("%.6g") produces in the C locale, without the locale / format-string machinery.
 void format_row(const double *row, size_t len, std::string &out)
 {
     out.clear();
     out.reserve(len * 12 + 2);
-    char t[40];
+    char t[48];
     for (size_t i = 0; i < len; ++i) {
-        const int n = snprintf(t, sizeof t, "%g", row[i]);
+        const double v = row[i];
         if (i) out.append(", ", 2);
-        out.append(t, (size_t)n);
+        if (v == 0.0 && !std::signbit(v)) { out.push_back('0'); continue; }
+        if (v > 0.0 && v < 100000.0 && v == (double)(int)v) {          // "%g" prints integers below 10^6 as plain digits
+            int k = (int)v, n = 0;
+            char d[8];
+            while (k) { d[n++] = (char)('0' + k % 10); k /= 10; }
+            while (n) out.push_back(d[--n]);
+            continue;
+        }
+        if (std::isfinite(v)) {
+            const auto r = std::to_chars(t, t + sizeof t, v, std::chars_format::general, 6);
+            out.append(t, (size_t)(r.ptr - t));
+        } else {
+            const int n = snprintf(t, sizeof t, "%g", v);                 // nan / inf spellings as printf has them
+            out.append(t, (size_t)n);
+        }
     }
     out.push_back('\n');
 }
@@ -147,3 +166,14 @@ SampleWriter::~SampleWriter()
 }
 
 }  // namespace brr
+
+// exposed for hosts and tests: the text of one sample row exactly as the writer emits it (without the trailing newline)
+extern "C" int64_t brr_format_row(const double *row, int64_t len, char *out, int64_t cap)
+{
+    if (!row || len < 0) return -1;
+    std::string text;
+    brr::format_row(row, (size_t)len, text);
+    const int64_t n = (int64_t)text.size() - 1;
+    if (out && cap > 0) { const int64_t c = n < cap - 1 ? n : cap - 1; memcpy(out, text.data(), (size_t)c); out[c] = 0; }
+    return n;
+}

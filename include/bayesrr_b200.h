@@ -193,6 +193,10 @@ int brr_chain_create_sharded(const brr_config *cfg, brr_geno *g, const brr_comm 
  * every rank's `token` */
 int brr_comm_selftest(const brr_comm *comm, double *buf, int64_t n, int64_t token, int64_t *gathered);
 
+/* Text of one sample row as the writer emits it: "%g" (6 significant digits) of every value joined by ", " (reference
+ * src/BayesRv2.cpp:72,266).  Returns the length without the terminating NUL (the text is truncated to cap - 1 characters); CPU only. */
+int64_t brr_format_row(const double *row, int64_t len, char *out, int64_t cap);
+
 /* Stand-alone kernels exposed for parity tests and roofline measurement.
  * gram: G[b][i][j] = sum_n code[n, order[b*B+i]] * code[n, order[b*B+j]]  (int32, nb x B x B; order index -1 = padding) */
 int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,

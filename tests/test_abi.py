@@ -75,3 +75,24 @@ def test_entry_point_iteration_validation_matches_reference(brr, tmp_path):
     except brr.BayesRRError as e:
         assert e.code == brr.E_ITER
     assert not out2.exists()
+
+
+def test_row_text_is_printf_g(brr):
+    """the writer's number formatting (fast paths + std::to_chars) against C's "%g" (what Eigen's IOFormat / ofstream precision 6 emit)"""
+    import numpy as np
+    lib = ctypes.CDLL(brr.LIB_PATH)
+    lib.brr_format_row.restype = ctypes.c_int64
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([
+        [0.0, -0.0, 1.0, 2.0, 3.0, 17.0, 99999.0, 100000.0, 999999.0, 1e6, 1234567.0, -5.0, 0.5, 1e-5, 1.5e-5, 123456.5, 0.1, 1 / 3,
+         2.5e-310, 1e300, -1e-300, np.inf, -np.inf, np.nan, 9.999995, 99999.95, 0.000123456789, 4503599627370496.0],
+        rng.normal(size=2000), rng.normal(size=500) * 1e-7, rng.normal(size=500) * 1e9, np.exp(rng.uniform(-700, 700, size=1000)),
+        np.round(rng.uniform(0, 2e6, size=300))])
+    buf = ctypes.create_string_buffer(64 * len(vals))
+    a = np.ascontiguousarray(vals, dtype=np.float64)
+    n = lib.brr_format_row(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_int64(len(a)), buf, ctypes.c_int64(len(buf)))
+    got = buf.value.decode().split(", ")
+    assert n == len(buf.value) and len(got) == len(vals)
+    want = ["%g" % v for v in vals]
+    bad = [(g, w) for g, w in zip(got, want) if g != w]
+    assert not bad, bad[:10]
