@@ -110,6 +110,26 @@ class Genotypes:
         return cls(h)
 
     @classmethod
+    def from_bed(cls, path, N=None, M=None, rows=None, impute_missing=False, device=0):
+        """PLINK 1 binary genotypes.  `path`: the .bed file or the common prefix of .bed/.bim/.fam; N, M default to the line counts
+        of the .fam / .bim files; rows = (row0, n_rows) reads one row shard."""
+        prefix = path[:-4] if path.endswith(".bed") else path
+        bed = prefix + ".bed"
+
+        def lines(p):
+            with open(p, "rb") as f:
+                return sum(1 for ln in f if ln.strip())
+        N = lines(prefix + ".fam") if N is None else N
+        M = lines(prefix + ".bim") if M is None else M
+        row0, n = rows if rows is not None else (0, 0)
+        h, miss = C.c_void_p(), C.c_int64()
+        _check(lib().brr_geno_from_bed(os.fsencode(bed), C.c_int64(N), C.c_int64(M), C.c_int64(row0), C.c_int64(n),
+                                       C.c_int(1 if impute_missing else 0), C.c_int(device), C.byref(h), C.byref(miss)))
+        g = cls(h)
+        g.n_missing = miss.value
+        return g
+
+    @classmethod
     def synthetic(cls, N, M, seed, row0=0, device=0):
         h = C.c_void_p()
         _check(lib().brr_geno_synthetic(C.c_int64(N), C.c_int64(M), C.c_uint64(seed), C.c_int64(row0), C.c_int(device), C.byref(h)))

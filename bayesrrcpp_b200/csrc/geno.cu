@@ -8,6 +8,10 @@
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace brr {
 
@@ -401,6 +405,98 @@ extern "C" int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_by
             upload_columns(g->d_packed, (size_t)g->stride, packed, (size_t)col_stride_bytes, (size_t)width, (size_t)M);
             stats_from_codes(g, mean, sd);
         } catch (...) { brr_geno_free(g); throw; }
+        *out = g;
+    });
+}
+
+// ---- PLINK .bed ingest.  The file is already 2 bits per genotype, SNP-major, four individuals per byte, low
+// bits first -- the layout of this store -- with another code book: 00 homozygous A1, 10 heterozygous, 11 homozygous A2,
+// 01 missing.  Codes here count A1 alleles (PLINK's additive coding): 00 -> 2, 10 -> 1, 11 -> 0, 01 -> 3 (missing, resolved below).
+__global__ void __launch_bounds__(256) bed_remap_kernel(uint8_t *__restrict__ packed, int64_t stride, int64_t N, int64_t M,
+                                                        unsigned long long *__restrict__ cnt /* [M][4]: n0, n1, n2, n_missing */)
+{
+    __shared__ unsigned long long s_n[4];
+    const int64_t col = blockIdx.x;
+    uint32_t *w = reinterpret_cast<uint32_t *>(packed + col * stride);
+    const int tid = threadIdx.x;
+    if (tid < 4) s_n[tid] = 0;
+    __syncthreads();
+    const int64_t nwords = stride / 4, full = N / 16;
+    unsigned long long n1 = 0, n2 = 0, n3 = 0;
+    for (int64_t i = tid; i < nwords; i += 256) {
+        const uint32_t v = w[i];
+        const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+        uint32_t c_hi = ~hi & ~lo & 0x55555555u, c_lo = hi & ~lo, miss = ~hi & lo & 0x55555555u;     // per 2-bit field, in the low bit
+        uint32_t keep = 0xffffffffu;                                                                 // fields of real individuals
+        if (i >= full) keep = (i == full && (N & 15)) ? ((1u << (2 * (N & 15))) - 1u) : 0u;
+        const uint32_t k1 = keep & 0x55555555u;
+        c_hi &= k1; c_lo &= k1; miss &= k1;
+        w[i] = (c_hi << 1) | c_lo | miss | (miss << 1);                                              // missing -> code 3 for now
+        n1 += __popc(c_lo); n2 += __popc(c_hi); n3 += __popc(miss);
+    }
+    atomicAdd(&s_n[1], n1); atomicAdd(&s_n[2], n2); atomicAdd(&s_n[3], n3);
+    __syncthreads();
+    if (tid < 4) cnt[col * 4 + tid] = tid == 0 ? (unsigned long long)N - s_n[1] - s_n[2] - s_n[3] : s_n[tid];
+}
+// missing genotypes -> the integer code nearest to the column's mean over the observed genotypes
+__global__ void __launch_bounds__(256) bed_impute_kernel(uint8_t *__restrict__ packed, int64_t stride, int64_t M,
+                                                         const unsigned long long *__restrict__ cnt)
+{
+    const int64_t col = blockIdx.x;
+    const unsigned long long n1 = cnt[col * 4 + 1], n2 = cnt[col * 4 + 2], nm = cnt[col * 4 + 3], n0 = cnt[col * 4];
+    if (nm == 0) return;
+    const unsigned long long obs = n0 + n1 + n2;
+    const uint32_t fill = obs ? (uint32_t)((double)(n1 + 2 * n2) / (double)obs + 0.5) : 0u;             // 0, 1 or 2
+    const uint32_t pat = fill * 0x55555555u;                                                             // the code in every field
+    uint32_t *w = reinterpret_cast<uint32_t *>(packed + col * stride);
+    for (int64_t i = threadIdx.x; i < stride / 4; i += 256) {
+        const uint32_t v = w[i];
+        const uint32_t m = v & (v >> 1) & 0x55555555u;          // fields holding 3
+        if (m) { const uint32_t mask = m | (m << 1); w[i] = (v & ~mask) | (pat & mask); }
+    }
+}
+
+extern "C" int brr_geno_from_bed(const char *bed_path, int64_t N_total, int64_t M, int64_t row0, int64_t N, int impute_missing,
+                                 int device, brr_geno **out, int64_t *n_missing)
+{
+    return guarded([&] {
+        BRR_REQUIRE(bed_path && out && N_total > 0 && M > 0, BRR_E_ARG, "brr_geno_from_bed: bad arguments");
+        if (N <= 0) { row0 = 0; N = N_total; }
+        BRR_REQUIRE(row0 >= 0 && row0 % 4 == 0 && row0 + N <= N_total, BRR_E_ARG, "row shard must start at a multiple of 4 and lie inside the file's individuals");
+        const int64_t width_total = (N_total + 3) / 4, width = (N + 3) / 4;
+        const int fd = open(bed_path, O_RDONLY);
+        BRR_REQUIRE(fd >= 0, BRR_E_IO, std::string("cannot open '") + bed_path + "'");
+        struct stat stt;
+        const bool ok_stat = fstat(fd, &stt) == 0;
+        const int64_t need = 3 + width_total * M;
+        if (!ok_stat || (int64_t)stt.st_size < need) { close(fd); throw Error(BRR_E_IO, std::string("'") + bed_path + "' is shorter than 3 + ceil(N/4) * M bytes: wrong N or M?"); }
+        void *map = mmap(nullptr, (size_t)need, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        BRR_REQUIRE(map != MAP_FAILED, BRR_E_IO, std::string("cannot map '") + bed_path + "'");
+        const uint8_t *file = static_cast<const uint8_t *>(map);
+        brr_geno *g = nullptr; unsigned long long *d_cnt = nullptr;
+        try {
+            BRR_REQUIRE(file[0] == 0x6c && file[1] == 0x1b, BRR_E_IO, "not a PLINK .bed file (magic number)");
+            BRR_REQUIRE(file[2] == 0x01, BRR_E_IO, "individual-major .bed files are not supported (re-export SNP-major: the PLINK 1.9 default)");
+            g = geno_alloc(N, M, device);
+            upload_columns(g->d_packed, (size_t)g->stride, file + 3 + row0 / 4, (size_t)width_total, (size_t)width, (size_t)M);
+            BRR_CUDA(cudaMalloc(&d_cnt, (size_t)M * 4 * sizeof(unsigned long long)));
+            bed_remap_kernel<<<(unsigned)M, 256>>>(g->d_packed, g->stride, N, M, d_cnt);
+            BRR_CUDA(cudaGetLastError());
+            std::vector<unsigned long long> cnt((size_t)M * 4);
+            BRR_CUDA(cudaMemcpy(cnt.data(), d_cnt, cnt.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            int64_t missing = 0;
+            for (int64_t j = 0; j < M; ++j) missing += (int64_t)cnt[(size_t)j * 4 + 3];
+            if (n_missing) *n_missing = missing;
+            if (missing > 0) {
+                BRR_REQUIRE(impute_missing != 0, BRR_E_GENO, std::to_string(missing) + " missing genotypes in '" + bed_path +
+                            "' (the reference has no notion of missing data; pass impute_missing to fill them with the rounded column mean)");
+                bed_impute_kernel<<<(unsigned)M, 256>>>(g->d_packed, g->stride, M, d_cnt);
+                BRR_CUDA(cudaGetLastError());
+            }
+            stats_from_codes(g, nullptr, nullptr);
+        } catch (...) { munmap(map, (size_t)need); cudaFree(d_cnt); brr_geno_free(g); throw; }
+        munmap(map, (size_t)need); cudaFree(d_cnt);
         *out = g;
     });
 }

@@ -81,6 +81,12 @@ int brr_geno_from_dense(const double *X, int64_t N, int64_t M, int device, brr_g
  * mean/sd NULL -> computed from the codes (sd with the N-1 denominator, like R scale()).       */
 int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_bytes, int64_t N, int64_t M,
                          const double *mean, const double *sd, int device, brr_geno **out);
+/* PLINK 1 .bed file (SNP-major) -> store, without a dense detour: N_total individuals and M markers as counted from the .fam / .bim
+ * files; rows [row0, row0 + N) of the file (row0 a multiple of 4; N <= 0: all rows) -- a row shard reads only its own bytes.
+ * Codes count A1 alleles (00 -> 2, 10 -> 1, 11 -> 0).  Missing genotypes (01): BRR_E_GENO unless impute_missing != 0, in which
+ * case they take the integer code nearest to the column mean of the observed genotypes; *n_missing (may be NULL) = how many. */
+int brr_geno_from_bed(const char *bed_path, int64_t N_total, int64_t M, int64_t row0, int64_t N, int impute_missing,
+                      int device, brr_geno **out, int64_t *n_missing);
 /* Device-side synthetic generator: g_ij ~ Binomial(2, p_j), p_j ~ U(0.05, 0.5), standardised.
  * Row sharding: this store holds rows [row0, row0+N) of a virtual N_total-row matrix (statistics are
  * computed over the local rows only until brr_geno_shard_stats is called).                      */

@@ -96,3 +96,21 @@ def test_row_text_is_printf_g(brr):
     want = ["%g" % v for v in vals]
     bad = [(g, w) for g, w in zip(got, want) if g != w]
     assert not bad, bad[:10]
+
+
+def test_bed_reader_reports_io_errors_before_touching_a_device(brr, tmp_path):
+    """missing / truncated / non-.bed files are BRR_E_IO (the file is checked first; no device is needed to find that out)"""
+    import pytest
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(str(tmp_path / "nope.bed"), N=10, M=10)
+    assert e.value.code == brr.E_IO
+    short = tmp_path / "short.bed"
+    short.write_bytes(bytes([0x6c, 0x1b, 0x01, 0, 0]))
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(str(short), N=100, M=100)
+    assert e.value.code == brr.E_IO and "shorter" in str(e.value)
+    notbed = tmp_path / "x.bed"
+    notbed.write_bytes(bytes(3 + 25 * 100))
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(str(notbed), N=100, M=100)
+    assert e.value.code == brr.E_IO and "magic" in str(e.value)

@@ -53,6 +53,70 @@ def test_from_packed_matches_dense_and_rejects_missing(po, brr):
     assert e.value.code == brr.E_GENO
 
 
+def _write_plink(prefix, codes, missing=None):
+    """codes: N x M counts of the A1 allele (0/1/2); missing: boolean N x M.  Writes prefix.bed/.bim/.fam (SNP-major)."""
+    N, M = codes.shape
+    bed = np.full((N, M), 0, dtype=np.uint8)
+    bed[codes == 2] = 0b00; bed[codes == 1] = 0b10; bed[codes == 0] = 0b11
+    if missing is not None:
+        bed[missing] = 0b01
+    width = (N + 3) // 4
+    out = np.zeros((M, width), dtype=np.uint8)
+    for q in range(4):
+        rows = np.arange(q, N, 4)
+        out[:, :len(rows)] |= (bed[rows, :].T << (2 * q)).astype(np.uint8)
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6c, 0x1b, 0x01])); f.write(out.tobytes())
+    with open(prefix + ".bim", "w") as f:
+        for j in range(M):
+            f.write("1\trs%d\t0\t%d\tA\tG\n" % (j, j + 1))
+    with open(prefix + ".fam", "w") as f:
+        for i in range(N):
+            f.write("F%d I%d 0 0 0 -9\n" % (i, i))
+
+
+def test_plink_bed_ingest(po, brr, tmp_path):
+    """SURVEY.md 8f-n1: .bed -> packed store without a dense detour; same store as from_dense on scale()d columns; row shards;
+    missing genotypes rejected or imputed to the rounded column mean"""
+    d = po.synth(1003, 140, seed=16)
+    prefix = str(tmp_path / "toy")
+    _write_plink(prefix, d["G"])
+    g = brr.Genotypes.from_bed(prefix)
+    assert (g.N, g.M, g.n_missing) == (1003, 140, 0)
+    assert np.array_equal(g.unpack(), d["G"])
+    st, ref = g.stats(), brr.Genotypes.from_dense(d["X"]).stats()
+    assert rel_inf(st["mean"], d["mean"]) < 1e-14 and rel_inf(st["sd"], d["sd"]) < 1e-13 and rel_inf(st["xsq"], ref["xsq"]) < 1e-12
+    eps = np.random.default_rng(2).normal(size=g.N)
+    assert rel_inf(g.xt_eps(eps)[0], d["X"].T @ eps) < 1e-12
+    # a row shard reads only its rows
+    sh = brr.Genotypes.from_bed(prefix + ".bed", rows=(512, 300))
+    assert np.array_equal(sh.unpack(), d["G"][512:812])
+    # missing genotypes
+    miss = np.zeros(d["G"].shape, dtype=bool)
+    miss[[3, 77, 500, 1002], [0, 0, 5, 139]] = True
+    _write_plink(prefix + "_m", d["G"], miss)
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(prefix + "_m")
+    assert e.value.code == brr.E_GENO and "4 missing" in str(e.value)
+    gi = brr.Genotypes.from_bed(prefix + "_m", impute_missing=True)
+    assert gi.n_missing == 4
+    got = gi.unpack()
+    want = d["G"].copy()
+    for i, j in zip(*np.nonzero(miss)):
+        obs = d["G"][~miss[:, j], j]
+        want[i, j] = int(obs.mean() + 0.5)
+    assert np.array_equal(got, want)
+    # not a .bed file / wrong dimensions
+    bad = tmp_path / "bad.bed"
+    bad.write_bytes(b"\x00\x01\x01" + bytes(5000))
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(str(bad), N=100, M=100)
+    assert e.value.code == brr.E_IO
+    with pytest.raises(brr.BayesRRError) as e:
+        brr.Genotypes.from_bed(prefix + ".bed", N=5000, M=140)
+    assert e.value.code == brr.E_IO
+
+
 def test_synthetic_store_is_row_shard_consistent(brr):
     whole = brr.Genotypes.synthetic(1024, 64, seed=5).unpack()
     lo = brr.Genotypes.synthetic(512, 64, seed=5, row0=0).unpack()
