@@ -315,6 +315,34 @@ def test_v2_chain_is_run_to_run_deterministic_and_resumable(po, brr):
     assert_trace_close("beta across geometries", V2Row(w, N, M).beta, V2Row(a, N, M).beta, TOL)
 
 
+def test_v2_full_size_residual_identity(brr):
+    """BASELINE config 2 size (N = M = 50,000; too large for the CPU oracle): the defining identity of the sampler's state,
+    eps = y - mu - X beta (reference src/BayesRv2.cpp:168,191,243), must hold after every iteration although eps is only ever
+    updated incrementally (block dots, look-ahead corrections, streamed deltas); components and beta must be consistent."""
+    N = M = 50000
+    g = brr.Genotypes.synthetic(N, M, seed=77)
+    rng = np.random.default_rng(3)
+    b = np.zeros(M); idx = rng.choice(M, 5000, replace=False); b[idx] = rng.normal(0, np.sqrt(0.5 / 5000), size=5000)
+    y = g.matvec(b) + rng.normal(0, np.sqrt(0.5), size=N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    T = 4
+    c = brr.Chain(g, brr.V2, T, seed=5, Y=y, cva=CVA, **HYP)
+    rows = c.run(T, emit_all=True)
+    r = V2Row(rows, N, M)
+    for t in range(T):
+        resid = y - r.mu[t] - g.matvec(r.beta[t])
+        assert rel_inf(r.eps[t], resid) < 1e-9, t
+        assert np.array_equal(r.comp[t] != 0, r.beta[t] != 0)          # component 0 <=> beta == 0 (:226-231)
+        assert set(np.unique(r.comp[t])) <= {0.0, 1.0, 2.0, 3.0}
+    assert (r.beta[-1] != 0).sum() > 100 and np.all(r.sigmaE > 0) and np.all(r.sigmaG > 0)
+    # the same chain with other geometry (64-marker blocks, fewer workers): assignments identical, traces within tolerance
+    c2 = brr.Chain(g, brr.V2, T, seed=5, Y=y, cva=CVA, block=64, workers=100, **HYP)
+    r2 = V2Row(c2.run(T, emit_all=True), N, M)
+    assert np.array_equal(r.comp, r2.comp)
+    assert_trace_close("beta across geometries", r2.beta, r.beta, TOL)
+    assert_trace_close("epsilon across geometries", r2.eps, r.eps, TOL)
+
+
 # ------------------------------------------------------------------------------------------------ Groups / restart
 def _groups_case(po, N, M, G, F, seed):
     d = po.synth(N, M, seed=seed)
