@@ -74,7 +74,6 @@ struct brr_chain {
     bool sweep_recorded[2] = {false, false};
     int64_t prepared_upto = -1;                      // marker order + Gram are in place for iterations <= this
     int gram_ctas = 0;
-    std::vector<int64_t> gram_timed;                 // iterations whose Gram events belong to the current brr_chain_run
     DevBuf<IterScalars> sc;
     DevBuf<int> abort_flag;
     DevBuf<long long> prof;
@@ -346,7 +345,6 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
     BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
     const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
     const size_t fo = (size_t)c->nb * c->B;
-    c->gram_timed.clear();
     // Marker order (host shuffle, reference :182) + block Gram of iteration j, on the Gram stream.  Called once per iteration,
     // in order, one iteration ahead of the sweep.
     auto prepare = [&](int64_t j) {
@@ -385,7 +383,6 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         if (c->prepared_upto < it) prepare(it);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
         BRR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gram1[gb], 0));
-        c->gram_timed.push_back(it);
         c->ll.zero(c->stream);
         BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
 

@@ -124,7 +124,8 @@ typedef struct brr_config {
     /* engine options; 0 = default */
     int block;                      /* markers per Gibbs block: 32, 64 or 128 (default 128) */
     int gram_impl;                  /* 0 = tcgen05 int8 tensor cores, 1 = dp4a CUDA cores (validation) */
-    int workers;                    /* worker CTAs of the persistent sweep kernel (default: SMs - 1) */
+    int workers;                    /* worker CTAs of the persistent sweep kernel (default: SMs - 1 - the SMs left to the Gram
+                                       kernel of the next iteration, which runs beside the sweep) */
     int speculate;                  /* reserved */
 } brr_config;
 
@@ -154,13 +155,15 @@ int brr_chain_get_pi(brr_chain *c, double *pi);
 int brr_chain_get_hyper(brr_chain *c, double *eta_tau_c2);
 /* device time (ms, CUDA events on the chain's stream) and kernel launches of the last brr_chain_run */
 int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches);
-/* device time (ms, CUDA events on the chain's stream) of the last brr_chain_run split by kernel: [0] block-Gram kernel,
- * [1] persistent sweep kernel, [2] hyper-parameter kernel(s); summed over the iterations of that run */
+/* device time (ms, CUDA events) of the last brr_chain_run split by kernel: [0] block-Gram kernel (on its own stream, beside the
+ * previous iteration's sweep: not on the critical path), [1] tables + persistent sweep kernel, [2] hyper-parameter kernel(s);
+ * summed over the iterations of that run */
 int brr_chain_kernel_ms(const brr_chain *c, double *gram_sweep_hyper_ms);
-/* SM-clock cycle accounting over the last brr_chain_run (16 values).  Sampler CTA: [0] gathering the workers' partial
- * dots, [1] speculative windows, [2] the whole serial in-block pass, [3] publishing the deltas, [4] number of windows,
- * [5] number of state-changing marker steps, [6] blocks, [7] cycles in state-changing steps.  First worker CTA:
- * [8] waiting for the deltas, [9] residual update, [10] dot stage + send */
+/* SM-clock cycle accounting over the last brr_chain_run (16 values).  Sampler CTA: [0] waiting for the workers' dots,
+ * [2] the whole serial in-block pass, [3] block set-up before it, [4] rounds of the walk, [5] state-changing marker steps,
+ * [6] blocks, [11] bookkeeping, [12] receiving a block's dots; with -DBRR_ROUND_PROFILE=1 also [9] threshold tests, [14] full
+ * draws + corrections, [15] sub-window prologues.  First worker CTA: [8] waiting for / applying deltas, [10] dot stage + send,
+ * [13] forming column totals */
 int brr_chain_sweep_profile(const brr_chain *c, double *out16);
 /* launch geometry chosen for the sweep kernel */
 int brr_chain_geometry(const brr_chain *c, int *block, int *workers, int *rows_per_worker_max, int *smem_bytes);
