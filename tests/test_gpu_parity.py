@@ -343,6 +343,44 @@ def test_v2_full_size_residual_identity(brr):
     assert_trace_close("epsilon across geometries", r2.eps, r.eps, TOL)
 
 
+def test_groups_full_size_residual_identity(brr):
+    """BASELINE config 3 size: BayesRSamplerV2Groups, N = 100,000 x M = 200,000, 22 groups, the vignette's N x 1 zero fixed matrix
+    (two 64-row words per lane in the workers): eps = y - mu - X beta - fixed alpha after every iteration"""
+    N, M, G, T = 100000, 200000, 22, 2
+    g = brr.Genotypes.synthetic(N, M, seed=78)
+    rng = np.random.default_rng(4)
+    b = np.zeros(M); idx = rng.choice(M, 2000, replace=False); b[idx] = rng.normal(0, np.sqrt(0.5 / 2000), size=2000)
+    y = g.matvec(b) + rng.normal(0, np.sqrt(0.5), size=N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    gA = (np.arange(M) * G // M).astype(np.int32)
+    cva = np.tile(np.array(CVA), (G, 1))
+    c = brr.Chain(g, brr.GROUPS, T, seed=6, Y=y, cva=cva, groups=G, gAssign=gA, fixed=np.zeros((N, 1)), **HYP)
+    assert c.geometry()["rows_per_worker_max"] > 512
+    r = GroupsRow(c.run(T, emit_all=True), N, M, G, 1)
+    for t in range(T):
+        keep = np.nonzero(r.beta[t])[0]
+        bt = np.zeros(M); bt[keep] = r.beta[t][keep]
+        assert rel_inf(r.eps[t], y - r.mu[t] - g.matvec(bt)) < 1e-9, t
+        assert np.array_equal(r.comp[t] != 0, r.beta[t] != 0)
+    assert np.all(r.sigmaG > 0) and np.all(r.sigmaE > 0) and r.sigmaG.shape == (T, G)
+
+
+def test_horseshoe_full_size_residual_identity(brr):
+    """BASELINE config 5 size: HorseshoeR, N = 100,000 x M = 100,000 (every marker moves every sweep)"""
+    N, M, T = 100000, 100000, 2
+    g = brr.Genotypes.synthetic(N, M, seed=79)
+    rng = np.random.default_rng(5)
+    b = np.zeros(M); idx = rng.choice(M, 1000, replace=False); b[idx] = rng.normal(0, np.sqrt(0.5 / 1000), size=1000)
+    y = g.matvec(b) + rng.normal(0, np.sqrt(0.5), size=N)
+    y = (y - y.mean()) / y.std(ddof=1)
+    p0 = 0.1 * M
+    c = brr.Chain(g, brr.HORSESHOE, T, seed=7, Y=y, A=(1 / np.sqrt(N)) * p0 / (M - p0), v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0)
+    r = HsRow(c.run(T, emit_all=True), N, M)
+    for t in range(T):
+        assert rel_inf(r.eps[t], y - r.mu[t] - g.matvec(r.beta[t])) < 1e-9, t
+    assert np.all(r.lam > 0) and np.all(r.tau > 0) and np.all(r.sigmaE > 0)
+
+
 # ------------------------------------------------------------------------------------------------ Groups / restart
 def _groups_case(po, N, M, G, F, seed):
     d = po.synth(N, M, seed=seed)
