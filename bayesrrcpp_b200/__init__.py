@@ -271,8 +271,19 @@ class Chain:
     def open_output(self, path):
         _check(lib().brr_chain_open_output(self._h, os.fsencode(path)))
 
+    def open_binary_output(self, path):
+        _check(lib().brr_chain_open_binary_output(self._h, os.fsencode(path)))
+
     def close_output(self):
         _check(lib().brr_chain_close_output(self._h))
+
+    def save(self, path):
+        """lossless checkpoint of the chain after its last completed iteration"""
+        _check(lib().brr_chain_save(self._h, os.fsencode(path)))
+
+    def load(self, path):
+        """continue the chain a checkpoint was taken from (call on a freshly created chain of the same configuration)"""
+        _check(lib().brr_chain_load(self._h, os.fsencode(path)))
 
     def run(self, n_iter, emit_all=False, max_rows=None):
         max_rows = n_iter if max_rows is None else max_rows
@@ -369,6 +380,17 @@ def HorseshoeR(outputFile, seed, max_iterations, burn_in, thinning, X, Y, A, v0E
                                 C.c_int(thinning), _p(X), C.c_int64(X.shape[0]), C.c_int64(X.shape[1]), _p(Y),
                                 C.c_double(A), C.c_double(v0E), C.c_double(s02E), C.c_double(vL), C.c_double(vT),
                                 C.c_double(c2), C.c_double(vC), C.c_double(sC)))
+
+
+def read_binary_samples(path):
+    """(meta, rows) of a file written through Chain.open_binary_output"""
+    with open(path, "rb") as f:
+        h = f.read(64)
+        assert h[:7] == b"BRRSMP1", "not a binary sample file"
+        kind, G = np.frombuffer(h, dtype=np.int32, count=2, offset=8)
+        N, M, F, L = np.frombuffer(h, dtype=np.int64, count=4, offset=16)
+        rows = np.fromfile(f, dtype=np.float64)
+    return dict(kind=int(kind), groups=int(G), N=int(N), M=int(M), F=int(F), row_len=int(L)), rows.reshape(-1, int(L))
 
 
 def lookahead(block):

@@ -85,7 +85,8 @@ struct brr_chain {
     std::vector<int32_t> rp_perm, rp_fixperm; std::vector<double> rp_init_u, rp_init_g, rp_mu_h, rp_gam_h, rp_nu_h;
     // rows
     RowSnap snaps[ROW_RING]; int64_t snap_seq = 0, deliver_seq = 0;
-    std::unique_ptr<SampleWriter> writer;
+    std::unique_ptr<SampleWriter> writer, bwriter;   // CSV (reference format) and binary (lossless fp64) sinks
+    int64_t restored_perm = -1;                      // brr_chain_load: markerI / fixedI already hold the order of this iteration
     int64_t it = 0; bool initialised = false;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0; int64_t last_launches = 0;
@@ -303,6 +304,7 @@ void deliver_row(brr_chain *c, RowSnap &s, double *rows, int64_t max_rows, int64
     const int64_t L = c->row_len();
     if (rows && *n_rows < max_rows) memcpy(rows + *n_rows * L, r, (size_t)L * 8);
     if (c->writer) c->writer->enqueue(r, (size_t)L);                                     // q.enqueue(sample)  :261
+    if (c->bwriter) c->bwriter->enqueue(r, (size_t)L);
     ++*n_rows;
     s.pending = false;
 }
@@ -352,11 +354,12 @@ void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_
         const int slot = (int)(j % PERM_RING), gb = (int)(j & 1);
         if (c->perm_used[slot]) BRR_CUDA(cudaEventSynchronize(c->perm_free[slot]));
         int32_t *hp = c->h_perm[slot].p;
+        const bool reshuffle = j != c->restored_perm;   // a loaded checkpoint already holds this iteration's order
         if (rp) memcpy(hp, &c->rp_perm[(size_t)j * M], (size_t)M * 4);
-        else { shuffle_host(c->key, S_PERM, j, c->markerI.data(), M); memcpy(hp, c->markerI.data(), (size_t)M * 4); }   // :182
+        else { if (reshuffle) shuffle_host(c->key, S_PERM, j, c->markerI.data(), M); memcpy(hp, c->markerI.data(), (size_t)M * 4); }   // :182
         if (F > 0) {
             if (rp) memcpy(hp + fo, &c->rp_fixperm[(size_t)j * F], (size_t)F * 4);
-            else { shuffle_host(c->key, S_FIXPERM, j, c->fixedI.data(), F); memcpy(hp + fo, c->fixedI.data(), (size_t)F * 4); }   // Groups:216
+            else { if (reshuffle) shuffle_host(c->key, S_FIXPERM, j, c->fixedI.data(), F); memcpy(hp + fo, c->fixedI.data(), (size_t)F * 4); }   // Groups:216
         }
         // the Gram buffer j & 1 was last read by the sweep of iteration j - 2
         if (c->sweep_recorded[gb]) BRR_CUDA(cudaStreamWaitEvent(c->gstream, c->ev_sweep_done[gb], 0));
@@ -616,7 +619,14 @@ extern "C" int brr_chain_open_output(brr_chain *c, const char *path)
 {
     return guarded([&] {
         BRR_REQUIRE(c && path, BRR_E_ARG, "null pointer");
-        c->writer.reset(new SampleWriter(path, sample_header(c->kind, c->N, c->M, c->G, c->F), c->kind != BRR_HORSESHOE));
+        c->writer.reset(new SampleWriter(path, sample_header(c->kind, c->N_total, c->M, c->G, c->F), c->kind != BRR_HORSESHOE));
+    });
+}
+extern "C" int brr_chain_open_binary_output(brr_chain *c, const char *path)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && path, BRR_E_ARG, "null pointer");
+        c->bwriter.reset(new SampleWriter(path, binary_sample_header(c->kind, c->N_total, c->M, c->G, c->F, c->row_len()), true, true));
     });
 }
 extern "C" int brr_chain_close_output(brr_chain *c)
@@ -624,6 +634,7 @@ extern "C" int brr_chain_close_output(brr_chain *c)
     return guarded([&] {
         BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
         if (c->writer) { std::unique_ptr<SampleWriter> w(std::move(c->writer)); w->finish(); }
+        if (c->bwriter) { std::unique_ptr<SampleWriter> w(std::move(c->bwriter)); w->finish(); }
     });
 }
 extern "C" int64_t brr_chain_row_len(const brr_chain *c) { return c ? c->row_len() : -1; }
@@ -637,6 +648,80 @@ extern "C" int brr_chain_run(brr_chain *c, int n_iter, int emit_all, double *row
         if (n_rows) *n_rows = produced;
     });
 }
+// ---- lossless checkpoint / resume for all four samplers (the reference restarts only the Groups model, from
+// 6-digit CSV text and without its draw state: src/BRv2Grstart.cpp:61-67).  The file holds everything the next iteration reads:
+// scalars, beta, components, residuals (this rank's rows), sigmaG, pi, alpha, lambda / nu, the marker order the in-place
+// shuffle has reached, and the iteration counter that keys the Philox draws -- a resumed chain continues bit for bit.
+namespace {
+struct CkptHeader {
+    char magic[8]; int32_t kind, K, G, world; int64_t N, N_total, M, F, it, perm_iter; uint64_t seed; int64_t sc_bytes;
+};
+template <class T> void put(FILE *f, const T *p, size_t n) { BRR_REQUIRE(fwrite(p, sizeof(T), n, f) == n, BRR_E_IO, "checkpoint write failed"); }
+template <class T> void get(FILE *f, T *p, size_t n) { BRR_REQUIRE(fread(p, sizeof(T), n, f) == n, BRR_E_IO, "checkpoint file is truncated"); }
+void d2h_put(FILE *f, const double *d, size_t n) { std::vector<double> h(n); if (n) BRR_CUDA(cudaMemcpy(h.data(), d, n * 8, cudaMemcpyDeviceToHost)); put(f, h.data(), n); }
+void get_h2d(FILE *f, double *d, size_t n) { std::vector<double> h(n); get(f, h.data(), n); if (n) BRR_CUDA(cudaMemcpy(d, h.data(), n * 8, cudaMemcpyHostToDevice)); }
+}  // namespace
+
+extern "C" int brr_chain_save(brr_chain *c, const char *path)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && path, BRR_E_ARG, "null pointer");
+        BRR_REQUIRE(!c->replay, BRR_E_ARG, "a chain driven by replay tables has no draw state to checkpoint");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        if (!c->initialised) chain_init(c);
+        BRR_CUDA(cudaStreamSynchronize(c->stream)); BRR_CUDA(cudaStreamSynchronize(c->gstream));
+        FILE *f = fopen(path, "wb");
+        BRR_REQUIRE(f, BRR_E_IO, std::string("cannot open checkpoint file '") + path + "'");
+        try {
+            CkptHeader h; memset(&h, 0, sizeof h);
+            memcpy(h.magic, "BRRCKP1", 7);
+            h.kind = c->kind; h.K = c->K; h.G = c->G; h.world = c->win.R; h.N = c->N; h.N_total = c->N_total; h.M = c->M; h.F = c->F;
+            h.it = c->it; h.perm_iter = c->prepared_upto; h.seed = c->seed; h.sc_bytes = (int64_t)sizeof(IterScalars);
+            put(f, &h, 1);
+            IterScalars sc; BRR_CUDA(cudaMemcpy(&sc, c->sc.p, sizeof sc, cudaMemcpyDeviceToHost));
+            put(f, &sc, 1);
+            const size_t M = (size_t)c->M, GK = (size_t)c->G * std::max(c->K, 1);
+            d2h_put(f, c->d_eps, (size_t)c->N); d2h_put(f, c->beta.p, M); d2h_put(f, c->comp.p, M);
+            d2h_put(f, c->sigmaG.p, (size_t)c->G); d2h_put(f, c->pi.p, GK); d2h_put(f, c->alpha.p, (size_t)c->F);
+            if (c->kind == BRR_HORSESHOE) { d2h_put(f, c->lambda.p, M); d2h_put(f, c->nu.p, M); }
+            put(f, c->markerI.data(), M); put(f, c->fixedI.data(), (size_t)c->F);
+        } catch (...) { fclose(f); throw; }
+        BRR_REQUIRE(fclose(f) == 0, BRR_E_IO, "checkpoint write failed");
+    });
+}
+
+extern "C" int brr_chain_load(brr_chain *c, const char *path)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && path, BRR_E_ARG, "null pointer");
+        BRR_REQUIRE(!c->replay, BRR_E_ARG, "a chain driven by replay tables cannot resume from a checkpoint");
+        BRR_REQUIRE(c->it == 0 && c->prepared_upto < 0, BRR_E_ARG, "load a checkpoint into a freshly created chain, before its first run");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        FILE *f = fopen(path, "rb");
+        BRR_REQUIRE(f, BRR_E_IO, std::string("cannot open checkpoint file '") + path + "'");
+        try {
+            CkptHeader h; get(f, &h, 1);
+            BRR_REQUIRE(memcmp(h.magic, "BRRCKP1", 7) == 0, BRR_E_IO, "not a checkpoint file");
+            BRR_REQUIRE(h.kind == c->kind && h.K == c->K && h.G == c->G && h.N == c->N && h.N_total == c->N_total && h.M == c->M && h.F == c->F &&
+                        h.world == c->win.R && h.sc_bytes == (int64_t)sizeof(IterScalars), BRR_E_ARG,
+                        "the checkpoint was written by a chain of another shape (sampler, components, groups, rows, markers, fixed effects or ranks)");
+            BRR_REQUIRE(h.seed == c->seed, BRR_E_ARG, "the checkpoint was written with another seed: the draws would not continue the chain");
+            if (!c->initialised) chain_init(c);
+            IterScalars sc; get(f, &sc, 1);
+            BRR_CUDA(cudaMemcpy(c->sc.p, &sc, sizeof sc, cudaMemcpyHostToDevice));
+            const size_t M = (size_t)c->M, GK = (size_t)c->G * std::max(c->K, 1);
+            get_h2d(f, c->d_eps, (size_t)c->N); get_h2d(f, c->beta.p, M); get_h2d(f, c->comp.p, M);
+            get_h2d(f, c->sigmaG.p, (size_t)c->G); get_h2d(f, c->pi.p, GK); get_h2d(f, c->alpha.p, (size_t)c->F);
+            if (c->kind == BRR_HORSESHOE) { get_h2d(f, c->lambda.p, M); get_h2d(f, c->nu.p, M); }
+            get(f, c->markerI.data(), M); get(f, c->fixedI.data(), (size_t)c->F);
+            c->it = h.it;
+            c->restored_perm = h.perm_iter;                   // markerI is the order OF that iteration: prepare() must not shuffle it again
+            c->prepared_upto = std::min<int64_t>(h.it - 1, h.perm_iter - 1);
+        } catch (...) { fclose(f); throw; }
+        fclose(f);
+    });
+}
+
 extern "C" int brr_chain_get_pi(brr_chain *c, double *pi)
 {
     return guarded([&] {
@@ -693,6 +778,7 @@ extern "C" void brr_chain_destroy(brr_chain *c)
 {
     if (!c) return;
     try { if (c->writer) c->writer->finish(); } catch (...) { }
+    try { if (c->bwriter) c->bwriter->finish(); } catch (...) { }
     delete c;
 }
 

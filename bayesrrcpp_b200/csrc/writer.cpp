@@ -110,10 +110,30 @@ void format_row(const double *row, size_t len, std::string &out)
     out.push_back('\n');
 }
 
-SampleWriter::SampleWriter(const std::string &path, const std::string &header, bool write_header_now)
-    : q_(8), header_(header)
+std::string binary_sample_header(int kind, int64_t N, int64_t M, int G, int64_t F, int64_t row_len)
 {
-    f_ = fopen(path.c_str(), "w");   // truncates like ofstream::open (src/BayesRv2.cpp:69)
+    std::string h(64, '\0');
+    memcpy(&h[0], "BRRSMP1", 7);
+    const int32_t k = kind, g = G;
+    memcpy(&h[8], &k, 4); memcpy(&h[12], &g, 4); memcpy(&h[16], &N, 8); memcpy(&h[24], &M, 8); memcpy(&h[32], &F, 8); memcpy(&h[40], &row_len, 8);
+    return h;
+}
+
+void SampleWriter::write_row(const std::vector<double> &row, std::string &text)
+{
+    if (binary_) {
+        if (fwrite(row.data(), 8, row.size(), f_) != row.size()) io_error_.store(true);
+    } else {
+        format_row(row.data(), row.size(), text);
+        if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
+    }
+    rows_written_.fetch_add(1);
+}
+
+SampleWriter::SampleWriter(const std::string &path, const std::string &header, bool write_header_now, bool binary)
+    : q_(8), header_(header), binary_(binary)
+{
+    f_ = fopen(path.c_str(), binary ? "wb" : "w");   // truncates like ofstream::open (src/BayesRv2.cpp:69)
     if (!f_) throw Error(BRR_E_IO, "cannot open output file '" + path + "'");
     if (write_header_now && !header_.empty()) { fwrite(header_.data(), 1, header_.size(), f_); header_.clear(); }
 }
@@ -127,14 +147,10 @@ void SampleWriter::start()
         std::vector<double> row; std::string text;
         while (true) {
             if (q_.try_dequeue(row)) {
-                format_row(row.data(), row.size(), text);
-                if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
-                rows_written_.fetch_add(1);
+                write_row(row, text);
             } else if (stop_.load(std::memory_order_acquire)) {
                 if (!q_.try_dequeue(row)) break;          // drained
-                format_row(row.data(), row.size(), text);
-                if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
-                rows_written_.fetch_add(1);
+                write_row(row, text);
             } else {
                 std::this_thread::yield();
             }

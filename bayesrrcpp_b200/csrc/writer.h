@@ -32,7 +32,8 @@ class SampleWriter {
 public:
     // write_header_now: V2 / Groups write the header before sampling starts (reference src/BayesRv2.cpp:70);
     // Horseshoe writes it from the consumer (src/HorseshoeR.cpp:275-291) -- same bytes either way.
-    SampleWriter(const std::string &path, const std::string &header, bool write_header_now);
+    // binary: rows are written as raw little-endian fp64 (lossless; `header` is then the binary file header, brr_sample_file_header)
+    SampleWriter(const std::string &path, const std::string &header, bool write_header_now, bool binary = false);
     ~SampleWriter();
     void start();
     void enqueue(const double *row, size_t len);
@@ -45,7 +46,11 @@ private:
     std::thread th_;
     std::atomic<bool> stop_{false}, io_error_{false};
     std::atomic<uint64_t> rows_written_{0};
-    bool running_ = false;
+    bool running_ = false, binary_ = false;
+    void write_row(const std::vector<double> &row, std::string &text);
 };
+
+// 64-byte header of the binary sample file: "BRRSMP1\0", int32 kind, int32 groups, int64 N, int64 M, int64 F, int64 row_len, zero padding
+std::string binary_sample_header(int kind, int64_t N, int64_t M, int G, int64_t F, int64_t row_len);
 
 }  // namespace brr

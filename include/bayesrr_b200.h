@@ -145,6 +145,14 @@ int brr_chain_create(const brr_config *cfg, brr_geno *g, brr_chain **out);
 int brr_chain_set_replay(brr_chain *c, const brr_replay *r);
 /* Append sample rows to `path` exactly like the reference writer (header written immediately). */
 int brr_chain_open_output(brr_chain *c, const char *path);
+/* Lossless sink beside (or instead of) the CSV: 64-byte header ("BRRSMP1\0", int32 kind, int32 groups, int64 N, M, F, row_len, zero
+ * padding) followed by the sample rows as raw little-endian fp64, reference row layout. */
+int brr_chain_open_binary_output(brr_chain *c, const char *path);
+/* Lossless checkpoint / resume for all four samplers: brr_chain_save writes the complete state after the last
+ * completed iteration; brr_chain_load, applied to a freshly created chain of the same configuration (same data, seed, shape)
+ * before its first run, makes it continue that chain bit for bit.  Row-sharded chains: one file per rank. */
+int brr_chain_save(brr_chain *c, const char *path);
+int brr_chain_load(brr_chain *c, const char *path);
 int64_t brr_chain_row_len(const brr_chain *c);
 /* Run n_iter further iterations.  rows (may be NULL): receives up to max_rows sample rows (reference row
  * layout) for kept iterations, or for every iteration when emit_all != 0; *n_rows = rows produced. */

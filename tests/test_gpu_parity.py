@@ -537,6 +537,54 @@ def test_entry_points_groups_restart_horseshoe_files(po, brr, tmp_path):
     assert len(rows3) == o3["n_rows"] == 2 and all(np.allclose(r, o3["rows"][i], rtol=2e-5, atol=1e-12) for i, r in enumerate(rows3))
 
 
+# ------------------------------------------------------------------------------------------------ binary sink, checkpoint / resume
+def test_binary_sink_is_lossless(po, brr, tmp_path):
+    """the binary file holds the sample rows bit for bit (the CSV keeps 6 significant digits)"""
+    N, M, T = 500, 130, 12
+    d = po.synth(N, M, seed=33)
+    g = brr.Genotypes.from_dense(d["X"])
+    c = brr.Chain(g, brr.V2, T, burn_in=2, thinning=3, seed=8, Y=d["y"], cva=CVA, **HYP)
+    c.open_output(str(tmp_path / "s.csv")); c.open_binary_output(str(tmp_path / "s.bin"))
+    rows = c.run(T)
+    c.close_output()
+    meta, got = brr.read_binary_samples(str(tmp_path / "s.bin"))
+    assert meta == dict(kind=brr.V2, groups=1, N=N, M=M, F=0, row_len=2 * M + 4 + N)
+    assert got.shape == rows.shape == (3, 2 * M + 4 + N) and np.array_equal(got, rows)        # iterations 3, 6, 9
+    _, text_rows = _parse(tmp_path / "s.csv")
+    assert len(text_rows) == 3 and np.allclose(text_rows[-1], rows[-1], rtol=2e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["v2", "groups", "horseshoe"])
+def test_checkpoint_resume_continues_the_chain_bit_for_bit(po, brr, tmp_path, kind):
+    """run 5 iterations, save, destroy; a fresh chain that loads the file produces exactly the rows the
+    uninterrupted chain produces (Philox draws are keyed by the iteration, the marker order is part of the state)"""
+    N, M, T, cut = 700, 300, 13, 5
+    if kind == "groups":
+        d, gA, cva, fixed = _groups_case(po, N, M, 3, 2, seed=95)
+        mk = lambda g: brr.Chain(g, brr.GROUPS, T, seed=21, Y=d["y"], cva=cva, groups=3, gAssign=gA, fixed=fixed, **HYP)
+    elif kind == "horseshoe":
+        d = po.synth(N, M, seed=96)
+        mk = lambda g: brr.Chain(g, brr.HORSESHOE, T, seed=22, Y=d["y"], A=0.03, v0E=1e-3, s02E=1e-3)
+    else:
+        d = po.synth(N, M, seed=97)
+        mk = lambda g: brr.Chain(g, brr.V2, T, seed=23, Y=d["y"], cva=CVA, **HYP)
+    g = brr.Genotypes.from_dense(d["X"])
+    whole = mk(g).run(T, emit_all=True)
+    a = mk(g)
+    first = a.run(cut, emit_all=True)
+    a.save(str(tmp_path / "chain.ckpt"))
+    a.close()
+    b = mk(g)
+    b.load(str(tmp_path / "chain.ckpt"))
+    rest = np.vstack([b.run(3, emit_all=True), b.run(T - cut - 3, emit_all=True)])
+    assert np.array_equal(first, whole[:cut]) and np.array_equal(rest, whole[cut:])
+    # a checkpoint of another chain is refused
+    other = brr.Chain(g, brr.V2, T, seed=99, Y=d["y"], cva=CVA, **HYP)
+    with pytest.raises(brr.BayesRRError) as e:
+        other.load(str(tmp_path / "chain.ckpt"))
+    assert e.value.code == brr.E_ARG
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors of the reference's own sources
 def _gold(name):
     import os
