@@ -46,6 +46,7 @@ struct RowSnap {            // one in-flight sample row
 
 struct brr_chain {
     brr_geno *g = nullptr;
+    int device = 0;                                               // g->device, kept here: the store may be freed before the chain
     int kind = 0, K = 0, G = 1; int64_t N = 0, M = 0, F = 0;     // N: rows of this rank
     int64_t N_total = 0;                                          // rows of all ranks (== N unless row-sharded)
     brr_comm comm{0, 1, nullptr, nullptr, nullptr};
@@ -105,7 +106,7 @@ struct brr_chain {
     }
     ~brr_chain()
     {
-        if (g) cudaSetDevice(g->device);
+        cudaSetDevice(device);
         for (auto &e : perm_free) if (e) cudaEventDestroy(e);
         for (auto &s : snaps) if (s.ready) cudaEventDestroy(s.ready);
         for (auto &e : kev) if (e) cudaEventDestroy(e);
@@ -501,7 +502,7 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         check_iters(cfg->max_iterations, cfg->burn_in, cfg->thinning);
         require_device(g->device);
         std::unique_ptr<brr_chain> c(new brr_chain());
-        c->g = g; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
+        c->g = g; c->device = g->device; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
         if (comm) c->comm = *comm;
         c->seed = cfg->seed; c->key = PhiloxKey{ (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32) };
         c->max_iterations = cfg->max_iterations; c->burn_in = cfg->burn_in; c->thinning = cfg->thinning;

@@ -32,9 +32,11 @@ void set_last_error(const std::string &m);
 // run `body`, translate exceptions into a return code + last-error string
 template <class F> int guarded(F &&body)
 {
+    // errors of earlier calls were reported by those calls: they must not surface again in this one's cudaGetLastError() checks
+    (void)cudaGetLastError();
     try { body(); return BRR_OK; }
-    catch (const Error &e) { set_last_error(e.what()); return e.code; }
-    catch (const std::exception &e) { set_last_error(e.what()); return BRR_E_ARG; }
+    catch (const Error &e) { set_last_error(e.what()); (void)cudaGetLastError(); return e.code; }
+    catch (const std::exception &e) { set_last_error(e.what()); (void)cudaGetLastError(); return BRR_E_ARG; }
 }
 
 // throws BRR_E_CUDA unless `device` exists and is compute capability 10.x; makes it current

@@ -139,6 +139,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--markers", type=int, default=CFG["M"], help="markers M (default: BASELINE configs[1]; 500000 with --gpus 8 = configs[3])")
+    ap.add_argument("--rows", type=int, default=CFG["N"], help="individuals per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--sampler", default="v2", choices=["v2", "groups", "horseshoe"],
+                    help="non-default samplers are for the other BASELINE shapes (configs[2]: groups 100000 x 200000, configs[4]: horseshoe 100000 x 100000)")
     ap.add_argument("--burn", type=int, default=CFG["chain_burn"], help="untimed chain burn-in iterations before the warm-up")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,13 +176,22 @@ def main():
             dist.all_reduce(t)
             a[:] = t.cpu().numpy()
     dev = local
-    N, M = CFG["N"], args.markers                      # N: rows per GPU
+    N, M = args.rows, args.markers                     # N: rows per GPU
     geno = brr.Genotypes.synthetic(N, M, CFG["data_seed"], row0=rank * N, device=dev)
     if comm is not None:
         geno.shard_stats(comm)
     y = simulate_phenotype(geno, CFG["data_seed"], CFG["h2"], CFG["causal_frac"], rank, host_allreduce)
     total_iters = args.burn + W + args.steps
-    chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, comm=comm, **CFG["hyp"])
+    if args.sampler == "groups":       # 22 chromosome-like groups, identical ladders, the vignette's N x 1 zero fixed matrix
+        G = 22
+        chain = brr.Chain(geno, brr.GROUPS, total_iters, seed=CFG["chain_seed"], Y=y, cva=np.tile(np.array(CFG["cva"]), (G, 1)), groups=G,
+                          gAssign=(np.arange(M) * G // M).astype(np.int32), fixed=np.zeros((N, 1)), block=args.block, comm=comm, **CFG["hyp"])
+    elif args.sampler == "horseshoe":
+        p0 = 0.1 * M
+        chain = brr.Chain(geno, brr.HORSESHOE, total_iters, seed=CFG["chain_seed"], Y=y, A=(1 / np.sqrt(N * world)) * p0 / (M - p0),
+                          v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=args.block, comm=comm)
+    else:
+        chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, comm=comm, **CFG["hyp"])
     chain.run_discard(args.burn)           # untimed chain burn-in: the timed steps see a settled sparsity pattern
     chain.run_discard(W)                           # warm-up steps
 
@@ -204,7 +216,7 @@ def main():
 
     # ---------------- end to end through the C ABI with host buffers (every rank; max time over ranks)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.sampler == "v2":
         codes = geno.codes()                                           # host packed genotypes (outside the timed region)
         st = geno.stats()
         thin = 5
@@ -260,7 +272,7 @@ def main():
     out = {"metric": "SNP-updates/sec", "value": value, "unit": "SNP-updates/s", "n_gpus": world, "steps": args.steps, "warmup": W,
            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": WORKLOAD if M == CFG["M"] else WORKLOAD.replace("M=50000", "M=%d" % M).replace("BASELINE configs[1]", "BASELINE configs[3] shape" if M == 500000 else "non-default M"), "block": geom["block"], "workers": geom["workers"],
+           "config": {"workload": ("%s N=%d x M=%d synthetic 2-bit genotypes (non-default sampler / shape)" % (args.sampler, N * world, M)) if (args.sampler != "v2" or N != CFG["N"]) else WORKLOAD if M == CFG["M"] else WORKLOAD.replace("M=50000", "M=%d" % M).replace("BASELINE configs[1]", "BASELINE configs[3] shape" if M == 500000 else "non-default M"), "block": geom["block"], "workers": geom["workers"],
                       "rows_per_worker_max": geom["rows_per_worker_max"], "chain_burn_in_iterations": args.burn,
                       "l2": "inputs larger than L2: %d MB of packed genotypes per GPU are re-read every step" % (M * ((N + 3) // 4) // 1000000),
                       "parallelism": "1 GPU" if world == 1 else
