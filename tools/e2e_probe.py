@@ -1,6 +1,8 @@
 import sys, time, tempfile, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, bayesrrcpp_b200 as brr
+if os.environ.get("PROBE_TORCH"):
+    import torch; torch.cuda.set_device(0); torch.zeros(1, device="cuda")
 N = M = 50000
 g = brr.Genotypes.synthetic(N, M, 7)
 y = np.random.default_rng(0).normal(size=N)
