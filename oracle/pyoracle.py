@@ -132,8 +132,11 @@ def _n_rows(max_it, burn_in, thinning, emit_all):
     return sum(1 for it in range(max_it) if it >= burn_in and it % thinning == 0)
 
 
+NATIVE = False     # bench.py's CPU arm switches to the -O3 -march=native build for its second measurement
+
+
 def _call(fn, args, source, seed, tables, record, n_rows, rowlen, want_rows=True):
-    L = lib()
+    L = lib(NATIVE)
     rows = np.zeros((n_rows, rowlen)) if want_rows else None
     got = C.c_int64(0)
     secs = C.c_double(0)
