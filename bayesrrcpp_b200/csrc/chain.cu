@@ -334,7 +334,21 @@ void snapshot_row(brr_chain *c, int64_t it, double *rows, int64_t max_rows, int6
     ++c->snap_seq;
 }
 
+void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows);
+
 void run_iterations(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows)
+{
+    try { run_iterations_body(c, n_iter, emit_all, rows, max_rows, n_rows); }
+    catch (...) {   // nothing of this call may still be in flight when the error reaches the caller (who may destroy the chain)
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->gstream) cudaStreamSynchronize(c->gstream);
+        for (auto &s : c->snaps) s.pending = false;
+        c->deliver_seq = c->snap_seq;
+        throw;
+    }
+}
+
+void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows)
 {
     BRR_CUDA(cudaSetDevice(c->g->device));
     if (!c->initialised) chain_init(c);

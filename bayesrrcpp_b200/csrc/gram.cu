@@ -335,12 +335,9 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
 #define BRR_GRAM_CASE(BB)                                                                                                   \
     if (B == BB) {                                                                                                          \
         if (impl == 0) {                                                                                                    \
-            static bool attr_set = false;                                                                                   \
-            if (!attr_set) {                                                                                                \
-                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
-                BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
-                attr_set = true;                                                                                            \
-            }                                                                                                               \
+            /* per device, and ranks may be threads: set on every launch (a cheap host-side call), no cached flag */       \
+            if (d_X) BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
+            else BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
             const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);                                \
             if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X); \
             else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr); \
