@@ -359,12 +359,21 @@ static void upload_columns(uint8_t *d_dst, size_t dpitch, const uint8_t *src, si
 {
     const size_t chunk_bytes = (size_t)16 << 20;
     const size_t cols_per = std::max<size_t>(1, chunk_bytes / dpitch);
-    uint8_t *buf[2] = { nullptr, nullptr }; cudaEvent_t ev[2] = { nullptr, nullptr }; cudaStream_t st = nullptr;
+    // the two pinned staging buffers are kept for the life of the process (pinning memory costs milliseconds per call and varies)
+    static std::mutex stage_mu;
+    static uint8_t *stage_buf[2] = { nullptr, nullptr };
+    static size_t stage_cap = 0;
+    std::lock_guard<std::mutex> stage_lock(stage_mu);
+    const size_t want = std::min(cols_per, ncols) * dpitch;
+    if (want > stage_cap) {
+        for (int i = 0; i < 2; ++i) { if (stage_buf[i]) cudaFreeHost(stage_buf[i]); stage_buf[i] = nullptr; }
+        stage_cap = 0;
+        for (int i = 0; i < 2; ++i) BRR_CUDA(cudaMallocHost(&stage_buf[i], std::max(want, chunk_bytes + dpitch)));
+        stage_cap = std::max(want, chunk_bytes + dpitch);
+    }
+    uint8_t *buf[2] = { stage_buf[0], stage_buf[1] }; cudaEvent_t ev[2] = { nullptr, nullptr }; cudaStream_t st = nullptr;
     try {
-        for (int i = 0; i < 2; ++i) {
-            BRR_CUDA(cudaMallocHost(&buf[i], std::min(cols_per, ncols) * dpitch));
-            BRR_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < 2; ++i) BRR_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
         BRR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         int i = 0; bool used[2] = { false, false };
         for (size_t c0 = 0; c0 < ncols; c0 += cols_per, i ^= 1) {
@@ -385,11 +394,11 @@ static void upload_columns(uint8_t *d_dst, size_t dpitch, const uint8_t *src, si
         }
         BRR_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
-        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+        for (int i = 0; i < 2; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
         if (st) cudaStreamDestroy(st);
         throw;
     }
-    for (int i = 0; i < 2; ++i) { cudaFreeHost(buf[i]); cudaEventDestroy(ev[i]); }
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ev[i]);
     cudaStreamDestroy(st);
 }
 

@@ -50,12 +50,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.all_rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
-    def __enter__(self):
+    def start(self):
+        """launch nvidia-smi early (its start-up takes a while and would otherwise fall into the timed region)"""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -63,12 +64,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.all_rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def __enter__(self):
+        if self.proc is None:
+            self.start()
+        self.t0 = time.time()
+        return self
 
     def __exit__(self, *a):
+        self.t1 = time.time()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.06)
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)      # gone before anything else is timed
+            except Exception:
+                pass
+
+    @property
+    def rows(self):
+        """samples taken inside the timed region (plus the one right after it when the region is shorter than the sampling period)"""
+        inside = [r for t, r in self.all_rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.05]
+        return inside if inside else [r for _, r in self.all_rows[-1:]]
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -207,6 +225,7 @@ def main():
                           v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=args.block, comm=comm)
     else:
         chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, comm=comm, **CFG["hyp"])
+    clk = ClockSampler(dev).start()        # nvidia-smi is up and sampling before the timed region begins
     chain.run_discard(args.burn)           # untimed chain burn-in: the timed steps see a settled sparsity pattern
     chain.run_discard(W)                           # warm-up steps
 
@@ -216,7 +235,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     barrier()
-    with ClockSampler(dev) as clk:
+    with clk:
         chain.run_discard(args.steps)              # timed: device time between CUDA events on the chain's stream
         barrier()
     ms, launches = chain.last_timing()
