@@ -11,7 +11,8 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libbayesrr_b200.so")
 SOURCES = ["geno.cu", "gram.cu", "sweep.cu", "hyper.cu", "shard.cu", "chain.cu", "writer.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DBRR_ROUND_PROFILE=1"] if os.environ.get("BRR_ROUND_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+FLAGS = (["-DBRR_ROUND_PROFILE=1"] if os.environ.get("BRR_ROUND_PROFILE") else []) + \
+        (["-DBRR_TENSOR_DOTS=1"] if os.environ.get("BRR_TENSOR_DOTS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 
 
