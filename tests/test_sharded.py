@@ -157,6 +157,48 @@ def test_sharded_horseshoe_thread_ranks(po, brr):
     assert np.all(np.abs(a.tau / b.tau - 1) <= TOL) and np.all(np.abs(a.sigmaE / b.sigmaE - 1) <= TOL)
 
 
+@pytest.mark.gpu
+def test_sharded_chain_from_bed_shards_with_checkpoint(po, brr, tmp_path):
+    """two ranks read their own rows of one PLINK .bed file, run a sharded chain, checkpoint it (one file per rank), and fresh
+    chains resumed from the files finish it: the whole thing equals the unsharded oracle run (assignments exact, 1e-9)"""
+    from test_gpu_parity import _write_plink
+    from bayesrrcpp_b200 import sharded
+    N, M, T, cut = 1400, 330, 10, 4
+    d = po.synth(N, M, seed=340)
+    prefix = str(tmp_path / "cohort")
+    _write_plink(prefix, 2 - d["G"])                 # the file counts the OTHER allele: codes = 2 - G, i.e. x -> -x after scaling
+    o = po.run_v2(-d["X"], d["y"], CVA, T, seed=341, **HYP)
+    bounds = sharded.shard_bounds(N, 2)
+
+    def run(first):
+        def fn(r, comm):
+            lo, hi = bounds[r]
+            g = brr.Genotypes.from_bed(prefix, rows=(lo, hi - lo)).shard_stats(comm)
+            c = brr.Chain(g, brr.V2, T, seed=341, Y=d["y"][lo:hi], cva=CVA, workers=12, comm=comm, **HYP)
+            ck = str(tmp_path / ("rank%d.ckpt" % r))
+            if first:
+                rows = c.run(cut, emit_all=True)
+                c.save(ck)
+            else:
+                c.load(ck)
+                rows = c.run(T - cut, emit_all=True)
+            c.close(); g.close()
+            return rows
+        try:
+            return sharded.ThreadGroup(2).run(fn)
+        except brr.BayesRRError as e:      # see _run_sharded: co-scheduling of the ranks' kernels on one device is not guaranteed
+            if "watchdog" not in str(e):
+                raise
+            return sharded.ThreadGroup(2).run(fn)
+    a, b = run(True), run(False)
+    assert np.array_equal(a[0], a[1]) and np.array_equal(b[0], b[1]), "ranks diverged"
+    got, want = V2Row(np.vstack([a[0], b[0]]), N, M), V2Row(o["rows"], N, M)
+    assert np.array_equal(got.comp, want.comp)
+    assert_trace_close("beta", got.beta, want.beta, TOL)
+    assert_trace_close("epsilon", got.eps, want.eps, TOL)
+    assert np.all(np.abs(got.sigmaE / want.sigmaE - 1) <= TOL) and np.all(np.abs(got.sigmaG / want.sigmaG - 1) <= TOL)
+
+
 # ------------------------------------------------------------------------------------------------ GPU: one process per device
 def _proc_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
