@@ -1,6 +1,7 @@
 // Host drivers of the four samplers: chain state in HBM, per-iteration launch sequence
-//   [host shuffle -> H2D]  gram kernel  ->  persistent sweep kernel  ->  hyper-parameter kernel(s)  [-> row snapshot D2H]
-// and the C ABI on top of it.  Mirrors the driver loops of the reference (src/BayesRv2.cpp:146-274,
+//   chain stream:  tables kernel -> persistent sweep kernel -> hyper-parameter kernel(s)  [-> row snapshot D2H]
+//   Gram stream:   [host shuffle -> H2D] -> block-Gram kernel (+ sum over ranks), one iteration ahead, beside the sweep
+// and the C ABI on top of it (entry points, sharded chains, sinks, checkpoints).  Mirrors the driver loops of the reference (src/BayesRv2.cpp:146-274,
 // src/BayesRv2Groups.cpp:170-333, src/BRv2Grstart.cpp:155-282, src/HorseshoeR.cpp:168-264); nothing here computes on
 // the CPU except initial scalars, the O(M) marker shuffle (std::random_shuffle in the reference, :182) and row packing.
 #include "sweep.cuh"
