@@ -325,7 +325,7 @@ def main():
            "state_changing_marker_fraction": prof["full_steps"] / (M * args.steps),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "algorithmic_bytes": algo_bytes, "kernel": "sweep_kernel", "peak_source": peak_src,
-                        "note": "serial Gibbs chain: the kernel is latency-bound (M dependent marker steps), see DESIGN.md 4"},
+                        "note": "serial Gibbs chain: the kernel is latency-bound (M dependent marker steps), see DESIGN.md 3.2"},
            "clocks": clk.summary()}
     if e2e:
         out["e2e"] = e2e
