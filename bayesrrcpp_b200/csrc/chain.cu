@@ -9,6 +9,9 @@
 #include "shard.cuh"
 #include "writer.h"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -19,19 +22,50 @@ namespace {
 
 constexpr int PERM_RING = 3, ROW_RING = 2;
 
+// chain_init carves the chain's buffers out of one device and one page-locked allocation: every cudaMalloc / cudaMallocHost
+// is a driver call of milliseconds (and a varying number of them), and a chain needs about thirty.  A buffer that does not
+// fit (or is allocated outside chain_init) falls back to its own allocation.
+struct Arena {
+    uint8_t *base = nullptr; size_t cap = 0, used = 0;
+    void *take(size_t bytes)
+    {
+        const size_t o = (used + 255) / 256 * 256;
+        if (!base || o + bytes > cap) return nullptr;
+        used = o + bytes;
+        return base + o;
+    }
+};
+thread_local Arena *t_dev_arena = nullptr, *t_pin_arena = nullptr;
+struct ArenaScope {
+    ArenaScope(Arena *d, Arena *h) { t_dev_arena = d; t_pin_arena = h; }
+    ~ArenaScope() { t_dev_arena = nullptr; t_pin_arena = nullptr; }
+};
+
 template <class T> struct DevBuf {
-    T *p = nullptr; size_t n = 0;
-    void alloc(size_t count) { release(); n = count; if (count) BRR_CUDA(cudaMalloc(&p, count * sizeof(T))); }
+    T *p = nullptr; size_t n = 0; bool owned = true;
+    void alloc(size_t count)
+    {
+        release(); n = count;
+        if (!count) return;
+        if (t_dev_arena) if (void *q = t_dev_arena->take(count * sizeof(T))) { p = static_cast<T *>(q); owned = false; return; }
+        BRR_CUDA(cudaMalloc(&p, count * sizeof(T))); owned = true;
+    }
     void zero(cudaStream_t s = 0) { if (p) BRR_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
     void upload(const T *h, size_t count) { if (count) BRR_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice)); }
     void from(const std::vector<T> &v) { alloc(v.size()); upload(v.data(), v.size()); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
     ~DevBuf() { release(); }
 };
 template <class T> struct PinBuf {
-    T *p = nullptr; size_t n = 0;
-    void alloc(size_t count) { release(); n = count; if (count) BRR_CUDA(cudaMallocHost(&p, count * sizeof(T))); }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+    T *p = nullptr; size_t n = 0; bool owned = true;
+    void alloc(size_t count)
+    {
+        release(); n = count;
+        if (!count) return;
+        if (t_pin_arena) if (void *q = t_pin_arena->take(count * sizeof(T))) { p = static_cast<T *>(q); owned = false; return; }
+        BRR_CUDA(cudaMallocHost(&p, count * sizeof(T))); owned = true;
+    }
+    void release() { if (p && owned) cudaFreeHost(p); p = nullptr; n = 0; owned = true; }
     ~PinBuf() { release(); }
 };
 
@@ -76,6 +110,7 @@ struct brr_chain {
     bool sweep_recorded[2] = {false, false};
     int64_t prepared_upto = -1;                      // marker order + Gram are in place for iterations <= this
     int gram_ctas = 0;
+    Arena dev_arena, pin_arena;                      // backing store of the buffers chain_init allocates
     DevBuf<IterScalars> sc;
     DevBuf<int> abort_flag;
     DevBuf<long long> prof;
@@ -117,6 +152,8 @@ struct brr_chain {
         if (gstream) cudaStreamDestroy(gstream);
         for (int i = 0; i < 2; ++i) { if (ev_gram0[i]) cudaEventDestroy(ev_gram0[i]); if (ev_gram1[i]) cudaEventDestroy(ev_gram1[i]); if (ev_sweep_done[i]) cudaEventDestroy(ev_sweep_done[i]); }
         win.release();
+        if (dev_arena.base) cudaFree(dev_arena.base);
+        if (pin_arena.base) cudaFreeHost(pin_arena.base);
     }
 };
 
@@ -182,6 +219,21 @@ void chain_init(brr_chain *c)
 {
     const int64_t N = c->N, M = c->M, F = c->F; const int K = c->K, G = c->G;
     BRR_CUDA(cudaSetDevice(c->g->device));
+    SetupTrace tr("chain_init");
+    {   // one device and one page-locked allocation for everything below (sizes: the large buffers exactly, the rest bounded)
+        const size_t gram_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
+        const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
+        const size_t tab = (size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F);
+        const size_t ll_words = (2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2;
+        const size_t dev_bytes = 2 * gram_ints * 4 + tab + PERM_RING * pn * 4 + 8 * (size_t)M * 8 + (size_t)N * F * 8 + ll_words * 8 +
+                                 ((size_t)G * (K + 2) * 3 + (size_t)F * (F + 3)) * 8 + 64 * 256 + ((size_t)1 << 16);
+        const size_t pin_bytes = PERM_RING * pn * 4 + ROW_RING * ((size_t)c->row_len() + sizeof(IterScalars) / 8 + 1 + (size_t)G) * 8 + 16 * 256;
+        if (!c->dev_arena.base) { BRR_CUDA(cudaMalloc(&c->dev_arena.base, dev_bytes)); c->dev_arena.cap = dev_bytes; }
+        if (!c->pin_arena.base) { BRR_CUDA(cudaMallocHost(&c->pin_arena.base, pin_bytes)); c->pin_arena.cap = pin_bytes; }
+        c->dev_arena.used = 0; c->pin_arena.used = 0;
+    }
+    ArenaScope arena_scope(&c->dev_arena, &c->pin_arena);
+    tr.mark("arenas (one cudaMalloc, one cudaMallocHost)");
     IterScalars sc; memset(&sc, 0, sizeof sc);
     std::vector<double> eps(c->g->Npad, 0.0), beta(M, 0.0), comp(M, 0.0), sigG(G, 0.0), pi((size_t)G * std::max(K, 1), 0.0);
     double mu = 0.0;
@@ -265,6 +317,7 @@ void chain_init(brr_chain *c)
         comm_allreduce(c->comm, fg.data(), (int64_t)fg.size());
         c->fixG.from(fg); c->alpha.from(al);
     }
+    tr.mark("initial state on the host and its upload");
     std::vector<IterScalars> scv(1, sc); c->sc.from(scv);
     c->ll.alloc((2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2); c->ll.zero();
     c->fin.alloc(2); c->fin.zero();
@@ -272,6 +325,7 @@ void chain_init(brr_chain *c)
     c->prof.alloc(16); c->prof.zero();
     for (auto &gb : c->gram) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
+    tr.mark("device buffers (hand-over words, Gram x2, tables)");
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
     for (int i = 0; i < PERM_RING; ++i) {
         c->h_perm[i].alloc(pn); c->d_perm[i].alloc(pn);
@@ -283,7 +337,9 @@ void chain_init(brr_chain *c)
         s.row.alloc((size_t)c->row_len()); s.scal.alloc(sizeof(IterScalars) / 8 + 1 + (size_t)G);
         BRR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     }
+    tr.mark("pinned rings (marker order, sample rows)");
     BRR_CUDA(cudaDeviceSynchronize());
+    tr.mark("device synchronize");
     c->initialised = true;
 }
 
@@ -516,6 +572,7 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         BRR_REQUIRE(cfg->kind >= BRR_V2 && cfg->kind <= BRR_HORSESHOE, BRR_E_ARG, "unknown sampler kind");
         check_iters(cfg->max_iterations, cfg->burn_in, cfg->thinning);
         require_device(g->device);
+        SetupTrace tr("chain_create");
         std::unique_ptr<brr_chain> c(new brr_chain());
         c->g = g; c->device = g->device; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
         if (comm) c->comm = *comm;
@@ -559,7 +616,9 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
                 c->eps0.assign(cfg->epsilon0, cfg->epsilon0 + N); c->comp0.assign(cfg->components0, cfg->components0 + M);
             }
         }
+        tr.mark("argument copies");
         choose_geometry(c.get(), cfg->block, cfg->workers);
+        tr.mark("geometry (occupancy queries)");
         const int R = c->comm.world;
         if (R > 1) {   // every rank must cut the chain into the same Gibbs blocks: agree on the smallest block any rank chose
             std::vector<double> bs(R, 0.0);
@@ -574,12 +633,14 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
             preload_tables(kidx); preload_gram(c->B, c->gram_impl); preload_hyper(c->kind);
             if (R > 1) preload_allsum();
         }
+        tr.mark("kernel preload");
         c->win.rank = c->comm.rank; c->win.R = R;
         c->win.layout(c->PS, c->nb, c->B, g->Npad);
         c->win.allocate();
         c->win.connect(c->comm, g->device, g->N, c->B, c->kind, c->M);
         c->N_total = c->win.n_total;
         c->d_eps = c->win.eps(c->win.rank);
+        tr.mark("exchange window");
         if (R > 1) BRR_REQUIRE((double)c->N_total == g->n_total, BRR_E_ARG,
                                "the genotype store of a sharded chain needs brr_geno_shard_stats first (its statistics must cover all ranks' rows)");
         BRR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -589,6 +650,7 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
             BRR_CUDA(cudaEventCreateWithFlags(&c->ev_sweep_done[i], cudaEventDisableTiming));
         }
         BRR_CUDA(cudaEventCreate(&c->ev0)); BRR_CUDA(cudaEventCreate(&c->ev1));
+        tr.mark("streams and events");
         *out = c.release();
     });
 }

@@ -1,5 +1,8 @@
 // Internal declarations shared by the translation units of libbayesrr_b200.so.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -50,6 +53,19 @@ template <class K> void preload_kernel(K *kernel)
     cudaFuncAttributes a;
     BRR_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void *>(kernel)));
 }
+
+// BRR_TRACE_SETUP=1: wall-clock milliseconds of the set-up stages on stderr (where the end-to-end time outside the iterations goes)
+struct SetupTrace {
+    bool on; const char *what; std::chrono::steady_clock::time_point t;
+    explicit SetupTrace(const char *w) : on(getenv("BRR_TRACE_SETUP") != nullptr), what(w), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *stage)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[brr setup] %s / %s: %.2f ms\n", what, stage, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 // Look-ahead depth of the sweep for Gibbs blocks of B markers: the deltas of the last lookahead(B) markers of a block reach the
 // next block through the cross-Gram correction instead of through the workers' dots (sweep.cu, gram.cu).

@@ -27,11 +27,15 @@ void require_device(int device)
         throw Error(BRR_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
                                     "): bayesrr_b200 has no CPU fallback");
     BRR_REQUIRE(device >= 0 && device < n, BRR_E_CUDA, "device index out of range");
-    cudaDeviceProp p;
-    BRR_CUDA(cudaGetDeviceProperties(&p, device));
-    BRR_REQUIRE(p.major == 10, BRR_E_CUDA,
-                std::string("device ") + p.name + " is sm_" + std::to_string(p.major) + std::to_string(p.minor) +
-                    "; this library is built for sm_100a (B200) only");
+    int major = 0, minor = 0;                     // two attribute reads: cudaGetDeviceProperties costs milliseconds per call
+    BRR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    BRR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (major != 10) {
+        cudaDeviceProp p;
+        BRR_CUDA(cudaGetDeviceProperties(&p, device));
+        throw Error(BRR_E_CUDA, std::string("device ") + p.name + " is sm_" + std::to_string(major) + std::to_string(minor) +
+                                    "; this library is built for sm_100a (B200) only");
+    }
     BRR_CUDA(cudaSetDevice(device));
 }
 
@@ -357,6 +361,14 @@ static void stats_from_codes(brr_geno *g, const double *mean, const double *sd)
 // chunk's staging.
 static void upload_columns(uint8_t *d_dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, size_t ncols)
 {
+    // page-locked source (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): the copy engine reads it in place
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        if (spitch == dpitch) BRR_CUDA(cudaMemcpy(d_dst, src, ncols * dpitch - (dpitch - width), cudaMemcpyHostToDevice));
+        else BRR_CUDA(cudaMemcpy2D(d_dst, dpitch, src, spitch, width, ncols, cudaMemcpyHostToDevice));
+        return;
+    }
+    (void)cudaGetLastError();
     const size_t chunk_bytes = (size_t)16 << 20;
     const size_t cols_per = std::max<size_t>(1, chunk_bytes / dpitch);
     // the two pinned staging buffers are kept for the life of the process (pinning memory costs milliseconds per call and varies)
@@ -409,10 +421,14 @@ extern "C" int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_by
         BRR_REQUIRE(packed && out, BRR_E_ARG, "brr_geno_from_packed: null pointer");
         const int64_t width = (N + 3) / 4;
         BRR_REQUIRE(col_stride_bytes >= width, BRR_E_ARG, "col_stride_bytes smaller than ceil(N/4)");
+        SetupTrace tr("geno_from_packed");
         brr_geno *g = geno_alloc(N, M, device);
+        tr.mark("device store (allocation, zero fill)");
         try {
             upload_columns(g->d_packed, (size_t)g->stride, packed, (size_t)col_stride_bytes, (size_t)width, (size_t)M);
+            tr.mark("host -> device copy of the packed columns");
             stats_from_codes(g, mean, sd);
+            tr.mark("per-marker statistics");
         } catch (...) { brr_geno_free(g); throw; }
         *out = g;
     });

@@ -8,12 +8,13 @@ rows [50,000 r, 50,000 (r+1)) of the same virtual matrix (weak scaling: fixed ro
 the per-block partial dots are exchanged over NVLink peer memory inside the sweep kernel.
 
   value     : whole-job SNP-updates/s, genotypes resident in HBM, device-timed (CUDA events on the chain's stream)
-  e2e       : same metric through the C ABI with HOST buffers: packed genotypes H2D, chain creation, per-iteration
-              permutation upload, sample rows D2H + CSV writer (thinning 10) all inside the timed region (wall clock)
+  e2e       : same metric through the C ABI with HOST buffers (page-locked): packed genotypes H2D, chain creation, per-iteration
+              permutation upload, sample rows D2H + CSV writer (thinning 5) all inside the timed region (wall clock)
   roofline  : the persistent sweep kernel against the measured HBM copy bandwidth (it is bound by the serial chain,
               not by HBM -- DESIGN.md section 4)
-  cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's Eigen sampler; R, Rcpp and Eigen are
-              absent, the reference itself cannot be built) on a bounded column sample of the same workload, 1 core.
+  cpu_baseline / --impl reference : the CPU oracle (C restatement of the reference's Eigen sampler, pinned against the
+              reference's own sources built over a minimal Eigen/Rcpp shim -- that shim is not a fair timing of Eigen, so the
+              port is what is timed) on a bounded column sample of the same workload, 1 core like the reference.
 """
 import argparse
 import json
@@ -251,7 +252,8 @@ def main():
     # ---------------- end to end through the C ABI with host buffers (every rank; max time over ranks)
     e2e = None
     if not args.no_e2e and args.sampler == "v2":
-        codes = geno.codes()                                           # host packed genotypes (outside the timed region)
+        codes_pinned = torch.from_numpy(geno.codes()).pin_memory()     # host packed genotypes, page-locked (outside the timed region)
+        codes = codes_pinned.numpy()
         st = geno.stats()
         thin = 5
         tmp = tempfile.NamedTemporaryFile(suffix=".csv", delete=False); tmp.close()

@@ -53,6 +53,25 @@ def test_from_packed_matches_dense_and_rejects_missing(po, brr):
     assert e.value.code == brr.E_GENO
 
 
+def test_from_packed_page_locked_source(po, brr):
+    """A page-locked host matrix is read in place by the copy engine (no staging): pitched and store-pitch sources."""
+    import torch
+    d = po.synth(1030, 70, seed=13)
+    N, M = d["G"].shape
+    ref = brr.Genotypes.from_dense(d["X"])
+    for cs in ((N + 3) // 4 + 3, ref.stride):
+        pinned = torch.zeros((M, cs), dtype=torch.uint8).pin_memory()
+        packed = pinned.numpy()
+        for q in range(4):
+            rows = np.arange(q, N, 4)
+            packed[:, :len(rows)] |= (d["G"][rows, :].T.astype(np.uint8) << (2 * q))
+        g = brr.Genotypes.from_packed(packed, N)
+        assert np.array_equal(g.codes(), ref.codes())
+        assert np.array_equal(g.unpack(), d["G"])
+        g.close()
+    ref.close()
+
+
 def _write_plink(prefix, codes, missing=None):
     """codes: N x M counts of the A1 allele (0/1/2); missing: boolean N x M.  Writes prefix.bed/.bim/.fam (SNP-major)."""
     N, M = codes.shape

@@ -7,6 +7,8 @@ N = M = 50000
 g = brr.Genotypes.synthetic(N, M, 7)
 y = np.random.default_rng(0).normal(size=N)
 codes = g.codes(); st = g.stats()
+if os.environ.get("PROBE_PINNED"):
+    import torch; keep = torch.from_numpy(codes).pin_memory(); codes = keep.numpy()
 hyp = dict(sigma0=0.01, v0E=1e-4, s02E=1e-3, v0G=1e-4, s02G=1e-3)
 for rep in range(2):
     t = [time.perf_counter()]
