@@ -24,6 +24,10 @@ def _deps():
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "flags.txt")             # a changed flag set (BRR_TENSOR_DOTS, BRR_ROUND_PROFILE) rebuilds everything
+    flags = " ".join(FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
     hdr_time = _deps()
     jobs = []
     for s in SOURCES:
@@ -48,6 +52,8 @@ def build(force=False, verbose=False):
     if verbose:
         for o in outs:
             sys.stderr.write(o)
+    with open(stamp, "w") as f:
+        f.write(flags)
     objs = [os.path.join(OBJ, s + ".o") for s in SOURCES]
     if jobs or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lpthread"]
