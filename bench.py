@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--workers", type=int, default=0, help="worker CTAs of the sweep kernel (default: the library's split of the SMs)")
     ap.add_argument("--markers", type=int, default=CFG["M"], help="markers M (default: BASELINE configs[1]; 500000 with --gpus 8 = configs[3])")
     ap.add_argument("--rows", type=int, default=CFG["N"], help="individuals per GPU (default: BASELINE configs[1])")
     ap.add_argument("--sampler", default="v2", choices=["v2", "groups", "horseshoe"],
@@ -219,13 +220,13 @@ def main():
     if args.sampler == "groups":       # 22 chromosome-like groups, identical ladders, the vignette's N x 1 zero fixed matrix
         G = 22
         chain = brr.Chain(geno, brr.GROUPS, total_iters, seed=CFG["chain_seed"], Y=y, cva=np.tile(np.array(CFG["cva"]), (G, 1)), groups=G,
-                          gAssign=(np.arange(M) * G // M).astype(np.int32), fixed=np.zeros((N, 1)), block=args.block, comm=comm, **CFG["hyp"])
+                          gAssign=(np.arange(M) * G // M).astype(np.int32), fixed=np.zeros((N, 1)), block=args.block, workers=args.workers, comm=comm, **CFG["hyp"])
     elif args.sampler == "horseshoe":
         p0 = 0.1 * M
         chain = brr.Chain(geno, brr.HORSESHOE, total_iters, seed=CFG["chain_seed"], Y=y, A=(1 / np.sqrt(N * world)) * p0 / (M - p0),
-                          v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=args.block, comm=comm)
+                          v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0, block=args.block, workers=args.workers, comm=comm)
     else:
-        chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, comm=comm, **CFG["hyp"])
+        chain = brr.Chain(geno, brr.V2, total_iters, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"], block=args.block, workers=args.workers, comm=comm, **CFG["hyp"])
     clk = ClockSampler(dev).start()        # nvidia-smi is up and sampling before the timed region begins
     chain.run_discard(args.burn)           # untimed chain burn-in: the timed steps see a settled sparsity pattern
     chain.run_discard(W)                           # warm-up steps
@@ -264,7 +265,7 @@ def main():
             g2.shard_stats(comm)
         t1 = time.perf_counter()
         c2 = brr.Chain(g2, brr.V2, args.steps, burn_in=1, thinning=thin, seed=CFG["chain_seed"], Y=y, cva=CFG["cva"],
-                       block=args.block, comm=comm, **CFG["hyp"])
+                       block=args.block, workers=args.workers, comm=comm, **CFG["hyp"])
         if rank == 0:
             c2.open_output(tmp.name)
         t2 = time.perf_counter()
