@@ -298,7 +298,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = None                                  # DRAM bytes of one sweep launch from the committed ncu --set full capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v6.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v8.json")) as f:
             k = [v for n, v in json.load(f).items() if "sweep_kernel" in n][0]
             traffic = int(1e6 * (float(k["dram__bytes_read.sum"]["value"]) + float(k["dram__bytes_write.sum"]["value"])))
     except Exception:
