@@ -323,7 +323,7 @@ def main():
                       "gibbs_iterations_per_s": 1e3 * args.steps / ms_max},
            "gpu_launches": int(launches),
            "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
-           "cycles_per_block": {k: prof[k] / max(prof["blocks"], 1) for k in ("gather", "serial_pass", "publish", "eval_cycles", "resolve_cycles", "prologue_cycles", "bookkeeping", "chunks_received", "worker_wait", "worker_dots", "worker_reduce")},
+           "cycles_per_block": {k: prof[k] / max(prof["blocks"], 1) for k in ("gather", "gather_first_chunk", "gather_last_chunk", "serial_pass", "publish", "eval_cycles", "resolve_cycles", "prologue_cycles", "bookkeeping", "chunks_received", "worker_wait", "worker_dots", "worker_reduce")},
            "markers_per_speculative_window": (M * args.steps) / max(prof["windows"], 1),
            "state_changing_marker_fraction": prof["full_steps"] / (M * args.steps),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
