@@ -38,7 +38,7 @@ class _Config(C.Structure):
                 ("mu0", C.c_double), ("beta0", _dp), ("sigmaE0", C.c_double), ("sigmaGG0", _dp),
                 ("epsilon0", _dp), ("components0", _dp),
                 ("A", C.c_double), ("vL", C.c_double), ("vT", C.c_double), ("c2", C.c_double), ("vC", C.c_double), ("sC", C.c_double),
-                ("block", C.c_int), ("gram_impl", C.c_int), ("workers", C.c_int), ("speculate", C.c_int)]
+                ("block", C.c_int), ("gram_impl", C.c_int), ("workers", C.c_int)]
 
 
 class _Replay(C.Structure):
@@ -382,6 +382,22 @@ def HorseshoeR(outputFile, seed, max_iterations, burn_in, thinning, X, Y, A, v0E
                                 C.c_double(c2), C.c_double(vC), C.c_double(sC)))
 
 
+_MSG_T = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+_msg_keep = None
+
+
+def set_message_handler(fn):
+    """fn(text) receives the reference's console messages ("iteration: <n>", "duration: <s>s"; src/BayesRv2.cpp:173-175,276-278)
+    from the four entry points; None silences them (the default)."""
+    global _msg_keep
+    L = lib()
+    L.brr_set_message_handler.restype = None
+    L.brr_set_message_handler.argtypes = [_MSG_T, C.c_void_p]
+    cb = _MSG_T(lambda ctx, text: fn(text.decode())) if fn is not None else C.cast(None, _MSG_T)
+    L.brr_set_message_handler(cb, None)
+    _msg_keep = cb
+
+
 def read_binary_samples(path):
     """(meta, rows) of a file written through Chain.open_binary_output"""
     with open(path, "rb") as f:
@@ -396,6 +412,13 @@ def read_binary_samples(path):
 def lookahead(block):
     """markers of a Gibbs block whose deltas reach the next block through the cross-Gram correction (csrc/common.cuh)"""
     return 64 if block >= 64 else 32
+
+
+def peak_fp64(device=0):
+    """measured fp64 FMA throughput (thread-level DFMAs per second)"""
+    v = C.c_double()
+    _check(lib().brr_peak_fp64(C.c_int(device), C.byref(v)))
+    return v.value
 
 
 def draws_sample(seed, stream, it, idx0, n, kind, shape=1.0):

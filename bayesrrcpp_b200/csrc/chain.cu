@@ -9,6 +9,7 @@
 #include "shard.cuh"
 #include "writer.h"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -20,7 +21,11 @@ using namespace brr;
 
 namespace {
 
-constexpr int PERM_RING = 3, ROW_RING = 2;
+constexpr int PERM_RING = 3, ROW_RING = 2, KEV_RING = 16;
+
+// the reference's console messages (header: brr_set_message_handler)
+std::atomic<brr_message_fn> g_msg_fn{nullptr};
+std::atomic<void *> g_msg_ctx{nullptr};
 
 // chain_init carves the chain's buffers out of one device and one page-locked allocation: every cudaMalloc / cudaMallocHost
 // is a driver call of milliseconds (and a varying number of them), and a chain needs about thirty.  A buffer that does not
@@ -72,6 +77,7 @@ template <class T> struct PinBuf {
 struct RowSnap {            // one in-flight sample row
     PinBuf<double> row;     // full row, reference layout
     PinBuf<double> scal;    // IterScalars (as bytes) followed by sigmaG[G]
+    PinBuf<int> abort;      // the in-kernel watchdog flag as of this snapshot: a row taken after it fired is never delivered
     cudaEvent_t ready = nullptr;
     bool pending = false;
     int64_t it = -1;
@@ -127,7 +133,9 @@ struct brr_chain {
     int64_t it = 0; bool initialised = false;
     cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0; int64_t last_launches = 0;
-    std::vector<cudaEvent_t> kev;            // 4 events per iteration: gram | sweep | hyper boundaries
+    // kernel timing: a fixed ring of KEV_RING iterations x 4 events (set-up | tables + sweep | hyper boundaries); a slot's
+    // times are read when the ring comes round to it again (the host never runs more than PERM_RING iterations ahead)
+    std::vector<cudaEvent_t> kev;
     double last_kernel_ms[3] = {0, 0, 0};
 
     int64_t row_len() const
@@ -227,7 +235,7 @@ void chain_init(brr_chain *c)
         const size_t ll_words = (2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2;
         const size_t dev_bytes = 2 * gram_ints * 4 + tab + PERM_RING * pn * 4 + 8 * (size_t)M * 8 + (size_t)N * F * 8 + ll_words * 8 +
                                  ((size_t)G * (K + 2) * 3 + (size_t)F * (F + 3)) * 8 + 64 * 256 + ((size_t)1 << 16);
-        const size_t pin_bytes = PERM_RING * pn * 4 + ROW_RING * ((size_t)c->row_len() + sizeof(IterScalars) / 8 + 1 + (size_t)G) * 8 + 16 * 256;
+        const size_t pin_bytes = PERM_RING * pn * 4 + ROW_RING * ((size_t)c->row_len() + sizeof(IterScalars) / 8 + 1 + (size_t)G) * 8 + 24 * 256;
         if (!c->dev_arena.base) { BRR_CUDA(cudaMalloc(&c->dev_arena.base, dev_bytes)); c->dev_arena.cap = dev_bytes; }
         if (!c->pin_arena.base) { BRR_CUDA(cudaMallocHost(&c->pin_arena.base, pin_bytes)); c->pin_arena.cap = pin_bytes; }
         c->dev_arena.used = 0; c->pin_arena.used = 0;
@@ -334,7 +342,7 @@ void chain_init(brr_chain *c)
     c->markerI.resize(M); for (int64_t i = 0; i < M; ++i) c->markerI[i] = (int32_t)i;   // :137-140
     c->fixedI.resize(F); for (int64_t i = 0; i < F; ++i) c->fixedI[i] = (int32_t)i;
     for (auto &s : c->snaps) {
-        s.row.alloc((size_t)c->row_len()); s.scal.alloc(sizeof(IterScalars) / 8 + 1 + (size_t)G);
+        s.row.alloc((size_t)c->row_len()); s.scal.alloc(sizeof(IterScalars) / 8 + 1 + (size_t)G); s.abort.alloc(1);
         BRR_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     }
     tr.mark("pinned rings (marker order, sample rows)");
@@ -343,9 +351,17 @@ void chain_init(brr_chain *c)
     c->initialised = true;
 }
 
+std::string watchdog_message(int flag)
+{
+    return "in-kernel watchdog fired (code " + std::to_string(flag) + ": 2 bulk copy, 3 Gram sum over ranks, 4 Gram bulk copy, 10-19 sweep hand-overs: "
+           "11 partial dots, 12 deltas, 13 flagged word, 14 fixed-effect totals, 15 block dots, 16 end-of-sweep sums, 17 fixed-point range, "
+           "18 / 19 look-ahead correction)";
+}
+
 void deliver_row(brr_chain *c, RowSnap &s, double *rows, int64_t max_rows, int64_t *n_rows)
 {
     BRR_CUDA(cudaEventSynchronize(s.ready));
+    BRR_REQUIRE(*s.abort.p == 0, BRR_E_CUDA, watchdog_message(*s.abort.p));       // no row of a chain whose sweep was aborted reaches a sink
     const int64_t N = c->N_total, M = c->M, F = c->F; const int G = c->G;
     IterScalars sc; memcpy(&sc, s.scal.p, sizeof sc);
     const double *sg = s.scal.p + sizeof(IterScalars) / 8 + 1;
@@ -386,6 +402,7 @@ void snapshot_row(brr_chain *c, int64_t it, double *rows, int64_t max_rows, int6
     }
     BRR_CUDA(cudaMemcpyAsync(s.scal.p, c->sc.p, sizeof(IterScalars), cudaMemcpyDeviceToHost, st));
     d2h(s.scal.p + sizeof(IterScalars) / 8 + 1, c->sigmaG.p, G);
+    BRR_CUDA(cudaMemcpyAsync(s.abort.p, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     BRR_CUDA(cudaEventRecord(s.ready, st));
     s.pending = true; s.it = it;
     ++c->snap_seq;
@@ -415,7 +432,15 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
     const int kk = c->kind == BRR_HORSESHOE ? 1 : K == 4 ? 2 : K == 3 ? 3 : 0;   // sweep-kernel variant
     int64_t launches = 0;
     c->prof.zero(c->stream);
-    while (c->kev.size() < (size_t)4 * n_iter) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
+    while (c->kev.size() < (size_t)4 * KEV_RING) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
+    c->last_kernel_ms[0] = c->last_kernel_ms[1] = c->last_kernel_ms[2] = 0;
+    auto harvest = [&](int slot) {      // add the kernel times of the iteration that used ring slot `slot`
+        BRR_CUDA(cudaEventSynchronize(c->kev[4 * slot + 3]));
+        for (int k = 1; k < 3; ++k) {
+            float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, c->kev[4 * slot + k], c->kev[4 * slot + k + 1]));
+            c->last_kernel_ms[k] += t;
+        }
+    };
     BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
     const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
     const size_t fo = (size_t)c->nb * c->B;
@@ -441,10 +466,10 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         BRR_CUDA(cudaEventRecord(c->ev_gram0[gb], c->gstream));
         if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
             int32_t *part = c->win.gram(c->win.rank, gb);
-            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->gstream, c->gram_ctas);
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->gstream, c->gram_ctas, c->abort_flag.p);
             launch_gram_allsum(c->win, gb, (uint32_t)j + 1u, c->gram[gb].p, all_ints, c->abort_flag.p, c->gstream, c->gram_ctas);
             ++launches;
-        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram[gb].p, c->gram[gb].p + self_ints, c->gstream, c->gram_ctas);
+        } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram[gb].p, c->gram[gb].p + self_ints, c->gstream, c->gram_ctas, c->abort_flag.p);
         BRR_CUDA(cudaEventRecord(c->ev_gram1[gb], c->gstream));
         c->prepared_upto = j;
         ++launches;
@@ -456,10 +481,12 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         if (rp) BRR_REQUIRE(it < c->rp_iters, BRR_E_ARG, "replay tables exhausted");
         const int slot = (int)(it % PERM_RING), gb = (int)(it & 1);
         if (c->prepared_upto < it) prepare(it);
-        BRR_CUDA(cudaEventRecord(c->kev[4 * n], c->stream));
+        const int ks = n % KEV_RING;
+        if (n >= KEV_RING) harvest(ks);
+        BRR_CUDA(cudaEventRecord(c->kev[4 * ks], c->stream));
         BRR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_gram1[gb], 0));
         c->ll.zero(c->stream);
-        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 1], c->stream));
+        BRR_CUDA(cudaEventRecord(c->kev[4 * ks + 1], c->stream));
 
         SweepParams p; memset(&p, 0, sizeof p);
         const brr_geno *g = c->g;
@@ -485,7 +512,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         p.gtab = c->gtab.p;
         launch_tables(kk, c->B, p, c->gtab.p, c->stream);
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
-        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 2], c->stream));
+        BRR_CUDA(cudaEventRecord(c->kev[4 * ks + 2], c->stream));
         BRR_CUDA(cudaEventRecord(c->perm_free[slot], c->stream));
         BRR_CUDA(cudaEventRecord(c->ev_sweep_done[gb], c->stream));
         c->sweep_recorded[gb] = true;
@@ -506,7 +533,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         h.tbl_hs_lam = rp && c->rp_lam.p ? c->rp_lam.p + (size_t)it * M : nullptr;
         h.tbl_hs_nu_next = next_in && c->rp_nu.p ? c->rp_nu.p + (size_t)(it + 1) * M : nullptr;
         launch_hyper(h, c->stream);
-        BRR_CUDA(cudaEventRecord(c->kev[4 * n + 3], c->stream));
+        BRR_CUDA(cudaEventRecord(c->kev[4 * ks + 3], c->stream));
         launches += 2 + hyper_launch_count(c->kind);
 
         if (emit_all || (it >= c->burn_in && it % c->thinning == 0))                     // :257-259
@@ -520,8 +547,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
     {
         int flag = 0;
         BRR_CUDA(cudaMemcpy(&flag, c->abort_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
-        BRR_REQUIRE(flag == 0, BRR_E_CUDA, "in-kernel watchdog fired (code " + std::to_string(flag) + ": 2 bulk copy, 3 Gram sum over ranks, 10-16 sweep hand-overs: "
-                    "11 partial dots, 12 deltas, 13 flagged word, 14 fixed-effect totals, 15 block dots, 16 end-of-sweep sums)");
+        BRR_REQUIRE(flag == 0, BRR_E_CUDA, watchdog_message(flag));
     }
     while (c->deliver_seq < c->snap_seq) {
         RowSnap &s = c->snaps[c->deliver_seq % ROW_RING];
@@ -530,12 +556,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
     }
     float ms = 0; BRR_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_ms = ms; c->last_launches = launches;
-    c->last_kernel_ms[0] = c->last_kernel_ms[1] = c->last_kernel_ms[2] = 0;
-    for (int n = 0; n < n_iter; ++n)
-        for (int k = 1; k < 3; ++k) {
-            float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, c->kev[4 * n + k], c->kev[4 * n + k + 1]));
-            c->last_kernel_ms[k] += t;
-        }
+    for (int n = std::max(0, n_iter - KEV_RING); n < n_iter; ++n) harvest(n % KEV_RING);
     // the Gram kernel runs beside the sweep of the previous iteration: its own duration is only known for the two most recent
     // preparations (their events are still in place); scale to the run
     {
@@ -571,6 +592,8 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         }
         BRR_REQUIRE(cfg->kind >= BRR_V2 && cfg->kind <= BRR_HORSESHOE, BRR_E_ARG, "unknown sampler kind");
         check_iters(cfg->max_iterations, cfg->burn_in, cfg->thinning);
+        BRR_REQUIRE(!g->pending_impute, BRR_E_ARG, "this .bed row shard still holds missing genotypes: brr_geno_shard_stats decides their fill "
+                    "value from the counts of all ranks and must be called first");
         require_device(g->device);
         SetupTrace tr("chain_create");
         std::unique_ptr<brr_chain> c(new brr_chain());
@@ -817,6 +840,16 @@ extern "C" int brr_chain_get_hyper(brr_chain *c, double *out)
         out[0] = sc.eta; out[1] = sc.tau; out[2] = sc.c2;
     });
 }
+extern "C" int brr_chain_get_sigmaE(brr_chain *c, double *sigmaE)
+{
+    return guarded([&] {
+        BRR_REQUIRE(c && sigmaE && c->initialised, BRR_E_ARG, "bad arguments");
+        BRR_CUDA(cudaSetDevice(c->g->device));
+        IterScalars sc; BRR_CUDA(cudaMemcpy(&sc, c->sc.p, sizeof sc, cudaMemcpyDeviceToHost));
+        *sigmaE = sc.sigmaE;
+    });
+}
+extern "C" void brr_set_message_handler(brr_message_fn fn, void *ctx) { g_msg_ctx.store(ctx); g_msg_fn.store(fn); }
 extern "C" int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches)
 {
     return guarded([&] {
@@ -877,14 +910,45 @@ void touch_file(const char *path, const std::string &header)
     fclose(f);
 }
 
+void say(const std::string &text)
+{
+    if (brr_message_fn fn = g_msg_fn.load()) fn(g_msg_ctx.load(), text.c_str());
+}
+std::string gfmt(double v) { char b[40]; snprintf(b, sizeof b, "%g", v); return b; }   // operator<<(double) of an ostream at its default precision
+
 void run_entry(const char *outputFile, const brr_config &cfg, const double *X, int64_t N, int64_t M)
 {
     GenoGuard gg; ChainGuard cg;
+    const auto t1 = std::chrono::steady_clock::now();
     check_rc(brr_geno_from_dense(X, N, M, 0, &gg.g));
     check_rc(brr_chain_create(&cfg, gg.g, &cg.c));
     check_rc(brr_chain_open_output(cg.c, outputFile));
-    check_rc(brr_chain_run(cg.c, cfg.max_iterations, 0, nullptr, 0, nullptr));
+    double h[3];
+    if (cfg.kind == BRR_HORSESHOE) {                                                    // src/HorseshoeR.cpp:191,195
+        check_rc(brr_chain_run(cg.c, 0, 0, nullptr, 0, nullptr));                       // initialisation only
+        check_rc(brr_chain_get_hyper(cg.c, h));
+        say("initial eta " + gfmt(h[0]) + "\n"); say("initial tau " + gfmt(h[1]) + "\n");
+    }
+    // The chain runs in chunks that end where the reference prints its progress line (src/BayesRv2.cpp:173-175: before iteration
+    // `it` when it > 0 and it % (max_iterations / 10) == 0; a period of 0 -- fewer than ten iterations, a division by zero there --
+    // counts as 1).  Every chunk boundary also checks the in-kernel watchdog, so an aborted chain stops within one chunk.
+    const int period = std::max(1, cfg.max_iterations / 10);
+    for (int it = 0; it < cfg.max_iterations; ) {
+        if (it > 0) {
+            say("iteration: " + std::to_string(it) + "\n");
+            if (cfg.kind == BRR_HORSESHOE) {                                            // src/HorseshoeR.cpp:203-206
+                double sE = 0;
+                check_rc(brr_chain_get_hyper(cg.c, h)); check_rc(brr_chain_get_sigmaE(cg.c, &sE));
+                say(" tau " + gfmt(h[1]) + "\n"); say(" eta " + gfmt(h[0]) + "\n"); say("sigmaE" + gfmt(sE) + "\n");
+            }
+        }
+        const int n = std::min(period, cfg.max_iterations - it);
+        check_rc(brr_chain_run(cg.c, n, 0, nullptr, 0, nullptr));
+        it += n;
+    }
     check_rc(brr_chain_close_output(cg.c));
+    const auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t1).count();
+    say("duration: " + std::to_string((long long)secs) + "s\n");                        // src/BayesRv2.cpp:276-278
 }
 
 }  // namespace

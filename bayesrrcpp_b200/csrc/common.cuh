@@ -85,6 +85,11 @@ struct brr_geno {
     double *d_a = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Q = nullptr, *d_xsq = nullptr, *d_csum = nullptr;
     std::vector<double> h_a, h_d, h_S, h_Q, h_xsq;
     double n_total = 0;            // rows the statistics refer to (== N unless sharded)
+    // A row shard of a .bed file with missing genotypes to impute: the fill value of a column is the rounded mean over the observed
+    // genotypes of ALL ranks, so the codes 3 stay in place (and the statistics undefined) until brr_geno_shard_stats has summed
+    // the per-column counts n0, n1, n2, n_missing (4 per marker) over the ranks.
+    bool pending_impute = false;
+    std::vector<double> pending_cnt;
 };
 
 namespace brr {
@@ -92,4 +97,6 @@ namespace brr {
 void geno_finalize_stats(brr_geno *g);
 // recompute a, d from S, Q and n_total (sd with the n_total - 1 denominator), then xsq / csum
 void geno_affine_from_stats(brr_geno *g);
+// resolve a pending imputation with the counts of all ranks (4 per marker), then the local code statistics
+void geno_impute_pending(brr_geno *g, const std::vector<double> &cnt_all);
 }

@@ -513,18 +513,47 @@ extern "C" int brr_geno_from_bed(const char *bed_path, int64_t N_total, int64_t 
             int64_t missing = 0;
             for (int64_t j = 0; j < M; ++j) missing += (int64_t)cnt[(size_t)j * 4 + 3];
             if (n_missing) *n_missing = missing;
-            if (missing > 0) {
-                BRR_REQUIRE(impute_missing != 0, BRR_E_GENO, std::to_string(missing) + " missing genotypes in '" + bed_path +
+            const bool shard = row0 != 0 || N != N_total;
+            if (missing > 0) BRR_REQUIRE(impute_missing != 0, BRR_E_GENO, std::to_string(missing) + " missing genotypes in '" + bed_path +
                             "' (the reference has no notion of missing data; pass impute_missing to fill them with the rounded column mean)");
-                bed_impute_kernel<<<(unsigned)M, 256>>>(g->d_packed, g->stride, M, d_cnt);
-                BRR_CUDA(cudaGetLastError());
+            if (impute_missing != 0 && shard) {
+                // the fill value is the rounded mean over the observed genotypes of the WHOLE column: decided in brr_geno_shard_stats,
+                // once the counts of all row shards are known (a shard without missing genotypes still contributes its counts)
+                g->pending_impute = true;
+                g->pending_cnt.assign(cnt.begin(), cnt.end());
+            } else {
+                if (missing > 0) {
+                    bed_impute_kernel<<<(unsigned)M, 256>>>(g->d_packed, g->stride, M, d_cnt);
+                    BRR_CUDA(cudaGetLastError());
+                }
+                stats_from_codes(g, nullptr, nullptr);
             }
-            stats_from_codes(g, nullptr, nullptr);
         } catch (...) { munmap(map, (size_t)need); cudaFree(d_cnt); brr_geno_free(g); throw; }
         munmap(map, (size_t)need); cudaFree(d_cnt);
         *out = g;
     });
 }
+
+namespace brr {
+void geno_impute_pending(brr_geno *g, const std::vector<double> &cnt_all)
+{
+    const int64_t M = g->M;
+    BRR_REQUIRE((int64_t)cnt_all.size() == 4 * M, BRR_E_ARG, "imputation counts do not match the store");
+    std::vector<unsigned long long> cnt((size_t)4 * M);
+    for (size_t i = 0; i < cnt.size(); ++i) cnt[i] = (unsigned long long)cnt_all[i];
+    unsigned long long *d_cnt = nullptr;
+    try {
+        BRR_CUDA(cudaMalloc(&d_cnt, cnt.size() * sizeof(unsigned long long)));
+        BRR_CUDA(cudaMemcpy(d_cnt, cnt.data(), cnt.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        // the kernel skips columns whose (global) missing count is zero; a column this shard has no missing genotype in is left as it is
+        bed_impute_kernel<<<(unsigned)M, 256>>>(g->d_packed, g->stride, M, d_cnt);
+        BRR_CUDA(cudaGetLastError());
+        stats_from_codes(g, nullptr, nullptr);
+    } catch (...) { cudaFree(d_cnt); throw; }
+    cudaFree(d_cnt);
+    g->pending_impute = false; g->pending_cnt.clear();
+}
+}  // namespace brr
 
 extern "C" int brr_geno_synthetic(int64_t N, int64_t M, uint64_t seed, int64_t row0, int device, brr_geno **out)
 {
@@ -556,6 +585,7 @@ extern "C" int brr_geno_stats(const brr_geno *g, double *mean, double *sd, doubl
 {
     return guarded([&] {
         BRR_REQUIRE(g, BRR_E_ARG, "null genotype store");
+        BRR_REQUIRE(!g->pending_impute, BRR_E_ARG, "statistics of a .bed row shard with missing genotypes exist only after brr_geno_shard_stats");
         const double n = g->n_total;
         for (int64_t j = 0; j < g->M; ++j) {
             if (mean) mean[j] = g->h_S[j] / n;
@@ -580,6 +610,7 @@ extern "C" int brr_geno_matvec(const brr_geno *g, const double *b, double *y)
 {
     return guarded([&] {
         BRR_REQUIRE(g && b && y, BRR_E_ARG, "null pointer");
+        BRR_REQUIRE(!g->pending_impute, BRR_E_ARG, "a .bed row shard with missing genotypes needs brr_geno_shard_stats first");
         BRR_CUDA(cudaSetDevice(g->device));
         std::vector<int32_t> cols; std::vector<double> vals;
         for (int64_t j = 0; j < g->M; ++j) if (b[j] != 0.0) { cols.push_back((int32_t)j); vals.push_back(b[j]); }
@@ -606,6 +637,7 @@ extern "C" int brr_xt_eps(const brr_geno *g, const double *eps, double *r, doubl
 {
     return guarded([&] {
         BRR_REQUIRE(g && eps && r, BRR_E_ARG, "null pointer");
+        BRR_REQUIRE(!g->pending_impute, BRR_E_ARG, "a .bed row shard with missing genotypes needs brr_geno_shard_stats first");
         BRR_CUDA(cudaSetDevice(g->device));
         double *d_eps = nullptr, *d_r = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
         try {
@@ -622,6 +654,46 @@ extern "C" int brr_xt_eps(const brr_geno *g, const double *eps, double *r, doubl
             BRR_CUDA(cudaMemcpy(r, d_r, g->M * 8, cudaMemcpyDeviceToHost));
         } catch (...) { cudaFree(d_eps); cudaFree(d_r); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
         cudaFree(d_eps); cudaFree(d_r); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    });
+}
+
+// ---- measured fp64 pipe peak: independent DFMA chains on every SM (the roofline the workers' dot stage is reported against)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int brr_peak_fp64(int device, double *dfma_per_s)
+{
+    return guarded([&] {
+        BRR_REQUIRE(dfma_per_s, BRR_E_ARG, "null pointer");
+        require_device(device);
+        int sms = 0;
+        BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int blocks = sms * 8, iters = 1 << 14;
+        double *d = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        try {
+            BRR_CUDA(cudaMalloc(&d, (size_t)blocks * 256 * 8));
+            BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
+            double best = 0.0;
+            for (int rep = 0; rep < 4; ++rep) {
+                BRR_CUDA(cudaEventRecord(e0));
+                fp64_peak_kernel<<<blocks, 256>>>(d, iters, 1.0 + rep);
+                BRR_CUDA(cudaEventRecord(e1));
+                BRR_CUDA(cudaGetLastError());
+                BRR_CUDA(cudaEventSynchronize(e1));
+                float ms = 0; BRR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep > 0) best = std::max(best, (double)blocks * 256 * 8 * iters / (ms * 1e-3));
+            }
+            *dfma_per_s = best;
+        } catch (...) { cudaFree(d); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
+        cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
     });
 }
 

@@ -30,8 +30,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait (~2 s): a lost completion must not hang the GPU; the result is then wrong and the parity tests say so
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// bounded wait (~2 s): a lost completion must not hang the GPU.  It raises the chain's sticky abort flag (code 4; the host turns
+// it into BRR_E_CUDA like every other in-kernel watchdog) and the kernel runs on to its end with a result nobody reads.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag)
 {
     const long long t0 = clock64();
     while (true) {
@@ -41,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) break;
-        if (clock64() - t0 > 4000000000LL) { __trap(); }
+        if (clock64() - t0 > 4000000000LL) { if (abort_flag) atomicCAS(abort_flag, 0, 4); break; }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
@@ -71,7 +72,7 @@ __device__ __forceinline__ uint4 expand16(uint32_t w)
 template <int B, bool CROSS>
 __global__ void __launch_bounds__(256, 1)
 gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
-               const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G, int32_t *__restrict__ X)
+               const int32_t *__restrict__ order, int64_t n_order, int32_t *__restrict__ G, int32_t *__restrict__ X, int *abort_flag)
 {
     static_assert(B == 32 || B == 64 || B == 128, "block size");
     constexpr int LA = lookahead(B);
@@ -138,12 +139,12 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
         int g = 0;                                   // running tile count: tile g uses operand buffer g & 1
         for (int L = 0; L < nloads; ++L) {
             const int s = L & 1;
-            mbar_wait(&full[s], (uint32_t)((L >> 1) & 1));
+            mbar_wait(&full[s], (uint32_t)((L >> 1) & 1), abort_flag);
             const uint8_t *stage = stage0 + s * R * GRAM_STAGE_ROW;
             const int nsub = load_rows(L) / GRAM_KC;
             for (int sub = 0; sub < nsub; ++sub, ++g) {
                 const int ts = g & 1;
-                if (g >= 2) mbar_wait(&freeb[ts], (uint32_t)(((g >> 1) - 1) & 1));     // the MMAs that read this buffer are done
+                if (g >= 2) mbar_wait(&freeb[ts], (uint32_t)(((g >> 1) - 1) & 1), abort_flag);     // the MMAs that read this buffer are done
                 uint8_t *tile = tile0 + ts * GRAM_TILE_BYTES;
                 // unpack: item = (v, c): 64 rows of marker c -> four 16-byte core-matrix rows
                 constexpr int ITEMS = R * (GRAM_KC / 64);
@@ -181,8 +182,8 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
         }
         {   // all MMAs done?  (commit groups complete in order: the last two cover both buffers)
             const int last = g - 1;
-            mbar_wait(&freeb[last & 1], (uint32_t)((last >> 1) & 1));
-            if (g > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1)); }
+            mbar_wait(&freeb[last & 1], (uint32_t)((last >> 1) & 1), abort_flag);
+            if (g > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1), abort_flag); }
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // epilogue: TMEM lane = marker row i, column = marker j
@@ -328,7 +329,7 @@ void preload_gram(int B, int impl)
 
 // launch on `stream`; G must hold nblocks * B * B int32
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
-                 int max_ctas)
+                 int max_ctas, int *abort_flag)
 {
 
     const int64_t nb = (n_order + B - 1) / B;
@@ -341,8 +342,8 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
             if (d_X) BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
             else BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
             const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);                                \
-            if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X); \
-            else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr); \
+            if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X, abort_flag); \
+            else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr, abort_flag); \
         } else {                                                                                                            \
             gram_dp4a_kernel<BB><<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G);      \
         }                                                                                                                   \
@@ -376,9 +377,9 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
             if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * lookahead(block) * block * 4));
             BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
-            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0);   // warm-up (module load, attribute)
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0, nullptr);   // warm-up (module load, attribute)
             BRR_CUDA(cudaEventRecord(e0));
-            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0);
+            launch_gram(g, d_order, n_order, block, impl, d_G, d_X, 0, 0, nullptr);
             BRR_CUDA(cudaEventRecord(e1));
             BRR_CUDA(cudaEventSynchronize(e1));
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;

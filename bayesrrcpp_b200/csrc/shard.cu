@@ -3,6 +3,7 @@
 #include "shard.cuh"
 #include <unistd.h>
 #include <cstring>
+#include <random>
 
 namespace brr {
 
@@ -17,6 +18,19 @@ void comm_allreduce(const brr_comm &comm, double *buf, int64_t n)
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// 64 random bits drawn once per process
+static uint64_t process_nonce()
+{
+    static const uint64_t nonce = [] {
+        std::random_device rd;
+        uint64_t v = ((uint64_t)rd() << 32) ^ (uint64_t)rd();
+        v ^= (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count() * 0x9E3779B97F4A7C15ull;
+        v ^= (uint64_t)getpid() << 17;
+        return v ? v : 1;
+    }();
+    return nonce;
+}
 
 void Window::layout(int PS, int nb, int B, int64_t Npad)
 {
@@ -40,20 +54,22 @@ void Window::allocate()
 void Window::connect(const brr_comm &comm, int device, int64_t n_local, int B, int kind, int64_t M)
 {
     PeerBlob mine; memset(&mine, 0, sizeof mine);
-    mine.pid = (int32_t)getpid(); mine.device = device; mine.base = (uint64_t)(uintptr_t)base;
+    mine.pid = (int32_t)getpid(); mine.nonce = process_nonce(); mine.device = device; mine.base = (uint64_t)(uintptr_t)base;
     mine.n_local = n_local; mine.block = B; mine.kind = kind; mine.M = M;
     if (R > 1) BRR_CUDA(cudaIpcGetMemHandle(&mine.handle, base));
     std::vector<PeerBlob> all(R);
     if (R > 1) comm_check(comm.allgather(comm.ctx, &mine, all.data(), (int64_t)sizeof(PeerBlob)), "allgather");
     else all[0] = mine;
-    BRR_REQUIRE(all[rank].pid == mine.pid && all[rank].base == mine.base, BRR_E_ARG, "brr_comm::allgather did not return this rank's own entry at index `rank`");
+    BRR_REQUIRE(all[rank].nonce == mine.nonce && all[rank].base == mine.base, BRR_E_ARG, "brr_comm::allgather did not return this rank's own entry at index `rank`");
     n_total = 0;
     for (int r = 0; r < R; ++r) {
         BRR_REQUIRE(all[r].block == B && all[r].kind == kind && all[r].M == M, BRR_E_ARG,
                     "ranks of a sharded chain disagree on the sampler, the number of markers or the Gibbs block size");
         n_rows[r] = all[r].n_local; row0[r] = n_total; n_total += all[r].n_local;
         if (r == rank) continue;
-        if (all[r].pid == mine.pid) {                 // same process (ranks are threads): the address is directly usable
+        // same process (ranks are threads): the address is directly usable.  Decided by a random per-process token, not by the pid
+        // alone -- ranks in different PID namespaces (one container per rank) can share a pid; anything else takes the IPC handle
+        if (all[r].nonce == mine.nonce && all[r].pid == mine.pid) {
             if (all[r].device != device) {
                 int can = 0;
                 BRR_CUDA(cudaDeviceCanAccessPeer(&can, device, all[r].device));
@@ -164,6 +180,16 @@ extern "C" int brr_geno_shard_stats(brr_geno *g, const brr_comm *comm)
         BRR_REQUIRE(comm->world >= 1 && comm->world <= BRR_MAX_WORLD, BRR_E_SIZE, "world size outside [1, " + std::to_string(BRR_MAX_WORLD) + "]");
         BRR_CUDA(cudaSetDevice(g->device));
         const int64_t M = g->M;
+        {   // missing genotypes of a .bed row shard: one fill value per column for all ranks (collective: every rank takes part)
+            double pending = g->pending_impute ? 1.0 : 0.0;
+            comm_allreduce(*comm, &pending, 1);
+            if (pending > 0.0) {
+                BRR_REQUIRE(g->pending_impute, BRR_E_ARG, "some ranks read their .bed row shard with impute_missing and some without");
+                std::vector<double> cnt = g->pending_cnt;
+                comm_allreduce(*comm, cnt.data(), (int64_t)cnt.size());      // integers below 2^53: exact in any order
+                geno_impute_pending(g, cnt);
+            }
+        }
         std::vector<double> buf((size_t)2 * M + 1);
         BRR_CUDA(cudaMemcpy(buf.data(), g->d_S, M * 8, cudaMemcpyDeviceToHost));
         BRR_CUDA(cudaMemcpy(buf.data() + M, g->d_Q, M * 8, cudaMemcpyDeviceToHost));

@@ -11,6 +11,7 @@ namespace brr {
 // What a rank tells the others about itself (all-gathered through brr_comm::allgather at creation).
 struct PeerBlob {
     int32_t pid, device;
+    uint64_t nonce;                // random per-process token: equal nonce and pid <=> the peer is a thread of this process
     uint64_t base;                 // device address of the window in the owner's address space
     cudaIpcMemHandle_t handle;     // for peers in other processes
     int64_t n_local;               // rows of this rank

@@ -93,7 +93,8 @@ int sweep_max_coresident(int kind, int B, int TW, size_t smem);
 
 // d_G: nb x B x B self products; d_X (nullable): nb x lookahead(B) x B products with the last lookahead(B) markers of the previous block
 // max_ctas > 0: persistent grid of at most that many CTAs (the tensor-core kernel loops over the blocks)
+// abort_flag (nullable): the chain's sticky watchdog flag (a lost bulk copy raises code 4)
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
-                 int max_ctas = 0);
+                 int max_ctas = 0, int *abort_flag = nullptr);
 
 }  // namespace brr

@@ -39,6 +39,13 @@ enum { BRR_V2 = 0, BRR_GROUPS = 1, BRR_GRSTART = 2, BRR_HORSESHOE = 3 };
 const char *brr_last_error(void);
 int brr_abi_version(void);
 
+/* The reference's console messages -- "iteration: <n>\n" whenever iteration % max(1, max_iterations / 10) == 0 and
+ * "duration: <s>s\n" at the end (src/BayesRv2.cpp:173-175,276-278, Rcpp::Rcout there; HorseshoeR also prints "initial eta",
+ * "initial tau" and tau / eta / sigmaE with every progress line, src/HorseshoeR.cpp:191,195,203-206) -- are handed to this
+ * call-back by the four entry points, on the calling thread.  NULL (the default): the messages are dropped.  Process-wide. */
+typedef void (*brr_message_fn)(void *ctx, const char *text);
+void brr_set_message_handler(brr_message_fn fn, void *ctx);
+
 /* ------------------------------------------------------------------------------------------------
  * The four reference entry points.  X is N x M column-major fp64 (what Rcpp hands over as
  * Eigen::MatrixXd); each column must take at most three equally spaced values (a standardised
@@ -84,7 +91,10 @@ int brr_geno_from_packed(const uint8_t *packed, int64_t col_stride_bytes, int64_
 /* PLINK 1 .bed file (SNP-major) -> store, without a dense detour: N_total individuals and M markers as counted from the .fam / .bim
  * files; rows [row0, row0 + N) of the file (row0 a multiple of 4; N <= 0: all rows) -- a row shard reads only its own bytes.
  * Codes count A1 alleles (00 -> 2, 10 -> 1, 11 -> 0).  Missing genotypes (01): BRR_E_GENO unless impute_missing != 0, in which
- * case they take the integer code nearest to the column mean of the observed genotypes; *n_missing (may be NULL) = how many. */
+ * case they take the integer code nearest to the column mean of the observed genotypes; *n_missing (may be NULL) = how many (in
+ * these rows).  A ROW SHARD read with impute_missing keeps its missing genotypes until brr_geno_shard_stats, which sums the
+ * per-column counts over the ranks first -- every rank fills with the same value, that of the unsharded file -- and the store
+ * can be used only after that call. */
 int brr_geno_from_bed(const char *bed_path, int64_t N_total, int64_t M, int64_t row0, int64_t N, int impute_missing,
                       int device, brr_geno **out, int64_t *n_missing);
 /* Device-side synthetic generator: g_ij ~ Binomial(2, p_j), p_j ~ U(0.05, 0.5), standardised.
@@ -126,7 +136,6 @@ typedef struct brr_config {
     int gram_impl;                  /* 0 = tcgen05 int8 tensor cores, 1 = dp4a CUDA cores (validation) */
     int workers;                    /* worker CTAs of the persistent sweep kernel (default: SMs - 1 - the SMs left to the Gram
                                        kernel of the next iteration, which runs beside the sweep) */
-    int speculate;                  /* reserved */
 } brr_config;
 
 /* Draw-replay tables (host memory, copied at set time).  Layout per iteration t in [0, n_iter):
@@ -161,6 +170,8 @@ int brr_chain_run(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t 
 int brr_chain_get_pi(brr_chain *c, double *pi);
 /* Horseshoe: eta, tau, c2 after the last completed iteration */
 int brr_chain_get_hyper(brr_chain *c, double *eta_tau_c2);
+/* residual variance after the last completed iteration */
+int brr_chain_get_sigmaE(brr_chain *c, double *sigmaE);
 /* device time (ms, CUDA events on the chain's stream) and kernel launches of the last brr_chain_run */
 int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches);
 /* device time (ms, CUDA events) of the last brr_chain_run split by kernel: [0] block-Gram kernel (on its own stream, beside the
@@ -225,6 +236,9 @@ int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, int64_t n_ord
                           int32_t *G_out, int32_t *X_out, double *ms);
 /* r[j] = sum_n x[n, j] * eps[n] for every marker (host eps N -> host r M), the streaming X^T eps kernel */
 int brr_xt_eps(const brr_geno *g, const double *eps, double *r, double *ms);
+/* measured fp64 FMA throughput of the device (thread-level DFMAs per second, independent chains on every SM): the roofline the
+ * workers' dot stage is reported against (bench.py) */
+int brr_peak_fp64(int device, double *dfma_per_s);
 /* counter-based draws exactly as the device code makes them (for generator parity tests) */
 int brr_draws_sample(uint64_t seed, int stream, int64_t it, int64_t idx0, int64_t n, int kind /*0 u, 1 z, 2 gamma*/,
                      double shape, double *out);

@@ -200,6 +200,8 @@ public:
     VectorXi() {}
     VectorXi(Index n) : d((size_t)n, 0) {}
     Index size() const { return (Index)d.size(); }
+    int *data() { return d.data(); }
+    const int *data() const { return d.data(); }
     int &operator()(Index i) { return d[(size_t)i]; }
     int operator()(Index i) const { return d[(size_t)i]; }
     int &operator[](Index i) { return d[(size_t)i]; }

@@ -114,3 +114,64 @@ def test_bed_reader_reports_io_errors_before_touching_a_device(brr, tmp_path):
     with pytest.raises(brr.BayesRRError) as e:
         brr.Genotypes.from_bed(str(notbed), N=100, M=100)
     assert e.value.code == brr.E_IO and "magic" in str(e.value)
+
+
+def test_rcpp_shim_compiles_with_the_reference_signatures_and_links(brr, tmp_path):
+    """shim/rcpp_shim.cpp (what a maintainer drops into the R package's src/) is compiled against the minimal Rcpp / Eigen
+    stand-ins the oracle's reference build uses (R, Rcpp and Eigen are absent here), its four functions are type-checked against
+    the reference's exact C++ signatures (src/RcppExports.cpp:10,39,61,86 declare them the same way) and the object is linked
+    against libbayesrr_b200.so, so every brr_* call it makes resolves with matching argument types."""
+    import subprocess
+    check = tmp_path / "check.cpp"
+    check.write_text(r'''
+#include <RcppEigen.h>
+#include <iostream>
+#include <string>
+namespace Eigen { void (*shim_row_hook)(const double *, long) = nullptr; }
+namespace Rcpp { std::ostream &Rcout = std::cout; std::ostream &Rcerr = std::cerr; }
+// declarations exactly as the reference's generated glue has them (src/RcppExports.cpp:10,39,61,86)
+void BRV2Grstart(std::string outputFile, int seed, int max_iterations, int burn_in, int thinning, double mu, Eigen::MatrixXd beta, double sigmaE, Eigen::VectorXd sigmaGG, Eigen::MatrixXd X, Eigen::VectorXd epsilon, Eigen::VectorXd components, double sigma0, double v0E, double s02E, double v0G, double s02G, Eigen::MatrixXd cva, int groups, Eigen::VectorXi gAssign);
+void BayesRSamplerV2(std::string outputFile, int seed, int max_iterations, int burn_in, int thinning, Eigen::MatrixXd X, Eigen::VectorXd Y, double sigma0, double v0E, double s02E, double v0G, double s02G, Eigen::VectorXd cva);
+void BayesRSamplerV2Groups(std::string outputFile, int seed, int max_iterations, int burn_in, int thinning, Eigen::MatrixXd X, Eigen::VectorXd Y, double sigma0, double v0E, double s02E, double v0G, double s02G, Eigen::MatrixXd cva, int groups, Eigen::VectorXi gAssign, Eigen::MatrixXd fixed);
+void HorseshoeR(std::string outputFile, int seed, int max_iterations, int burn_in, int thinning, Eigen::MatrixXd X, Eigen::VectorXd Y, double A, double v0E, double s02E, double vL, double vT, double c2, double vC, double sC);
+int main(int argc, char **)
+{
+    if (argc > 100) {   // never executed: the calls only have to compile and link
+        Eigen::MatrixXd X(4, 2); Eigen::VectorXd v(4); Eigen::VectorXi g(2);
+        BayesRSamplerV2("o", 1, 2, 1, 1, X, v, 0.01, 1e-4, 1e-3, 1e-4, 1e-3, v);
+        BayesRSamplerV2Groups("o", 1, 2, 1, 1, X, v, 0.01, 1e-4, 1e-3, 1e-4, 1e-3, X, 1, g, X);
+        BRV2Grstart("o", 1, 2, 1, 1, 0.0, X, 1.0, v, X, v, v, 0.01, 1e-4, 1e-3, 1e-4, 1e-3, X, 1, g);
+        HorseshoeR("o", 1, 2, 1, 1, X, v, 0.1, 1e-3, 1e-3, 1.0, 1.0, 1.0, 10.0, 10.0);
+    }
+    std::cout << "linked\\n";
+    return 0;
+}
+''')
+    exe = tmp_path / "shim_check"
+    libdir = os.path.dirname(brr.LIB_PATH)
+    cmd = ["g++", "-std=c++11", "-Wall", "-Werror=return-type", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "shim", "rcpp_shim.cpp"), str(check), "-L" + libdir, "-l:libbayesrr_b200.so", "-Wl,-rpath," + libdir,
+           "-Wl,--no-undefined", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    nm = subprocess.run(["nm", "-C", "--defined-only", str(exe)], capture_output=True, text=True).stdout
+    for f in ("BayesRSamplerV2(", "BayesRSamplerV2Groups(", "BRV2Grstart(", "HorseshoeR("):
+        assert f in nm, f
+    und = subprocess.run(["nm", "-C", "--undefined-only", str(exe)], capture_output=True, text=True).stdout
+    for f in ("brr_BayesRSamplerV2", "brr_BayesRSamplerV2Groups", "brr_BRV2Grstart", "brr_HorseshoeR", "brr_set_message_handler", "brr_last_error"):
+        assert f in und, f
+    out = subprocess.run([str(exe)], capture_output=True, text=True)        # loads libbayesrr_b200.so (and the CUDA runtime in it)
+    assert out.returncode == 0 and "linked" in out.stdout, out.stderr
+
+
+def test_message_handler_is_exported_and_silent_by_default(brr):
+    import ctypes as C
+    L = brr.lib()
+    FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+    got = []
+    cb = FN(lambda ctx, text: got.append(text))
+    L.brr_set_message_handler.restype = None
+    L.brr_set_message_handler.argtypes = [FN, C.c_void_p]
+    L.brr_set_message_handler(cb, None)
+    L.brr_set_message_handler(C.cast(None, FN), None)
+    assert got == []

@@ -529,6 +529,32 @@ def test_entry_point_v2_writes_the_reference_file(po, brr, tmp_path):
         assert same >= 0.999 * len(want)            # "%g" text equal except for values straddling a rounding boundary
 
 
+def test_entry_points_emit_the_reference_messages(po, brr, tmp_path):
+    """src/BayesRv2.cpp:173-175,276-278: "iteration: <n>" before every iteration n > 0 with n % (max_iterations / 10) == 0 and
+    "duration: <s>s" at the end; HorseshoeR adds "initial eta" / "initial tau" and tau / eta / sigmaE lines (HorseshoeR.cpp:191-206)"""
+    N, M = 300, 60
+    d = po.synth(N, M, seed=35)
+    got = []
+    brr.set_message_handler(got.append)
+    try:
+        brr.BayesRSamplerV2(str(tmp_path / "m.csv"), 1, 45, 10, 5, d["X"], d["y"], 0.01, 1e-4, 1e-3, 1e-4, 1e-3, CVA)
+        assert got[:-1] == ["iteration: %d\n" % i for i in range(4, 45, 4)]
+        assert got[-1].startswith("duration: ") and got[-1].endswith("s\n")
+        del got[:]
+        brr.HorseshoeR(str(tmp_path / "mh.csv"), 1, 20, 10, 5, d["X"], d["y"], 0.05, 1e-3, 1e-3, 1.0, 1.0, 1.0, 10.0, 10.0)
+        assert got[0].startswith("initial eta ") and got[1].startswith("initial tau ")
+        assert got[2:6] == ["iteration: 2\n"] + got[3:6] and got[3].startswith(" tau ") and got[4].startswith(" eta ") and got[5].startswith("sigmaE")
+        assert sum(1 for g in got if g.startswith("iteration: ")) == 9 and got[-1].startswith("duration: ")
+        o = po.run_horseshoe(d["X"], d["y"], 0.05, 20, burn_in=10, thinning=5, seed=1, emit_all=False)
+        rows = [np.array([float(x) for x in ln.split(", ")]) for ln in open(tmp_path / "mh.csv").read().split("\n")[1:-1]]
+        assert len(rows) == 2 and all(np.allclose(r, o["rows"][i], rtol=2e-5, atol=1e-12) for i, r in enumerate(rows))   # chunked run == one run
+    finally:
+        brr.set_message_handler(None)
+    del got[:]
+    brr.BayesRSamplerV2(str(tmp_path / "m2.csv"), 1, 12, 2, 5, d["X"], d["y"], 0.01, 1e-4, 1e-3, 1e-4, 1e-3, CVA)
+    assert got == []
+
+
 def test_entry_points_groups_restart_horseshoe_files(po, brr, tmp_path):
     N, M, G, F = 300, 70, 2, 2
     d, gA, cva, fixed = _groups_case(po, N, M, G, F, seed=90)

@@ -199,8 +199,65 @@ def test_sharded_chain_from_bed_shards_with_checkpoint(po, brr, tmp_path):
     assert np.all(np.abs(got.sigmaE / want.sigmaE - 1) <= TOL) and np.all(np.abs(got.sigmaG / want.sigmaG - 1) <= TOL)
 
 
+@pytest.mark.gpu
+def test_bed_row_shards_impute_missing_genotypes_like_the_whole_file(po, brr, tmp_path):
+    """a missing genotype is filled with the rounded mean over the observed genotypes of the WHOLE column, whatever the sharding
+    (per-shard means made the data depend on the world size)"""
+    from test_gpu_parity import _write_plink
+    from bayesrrcpp_b200 import sharded
+    N, M = 1200, 90
+    rng = np.random.default_rng(7)
+    G = np.zeros((N, M), dtype=np.int8)
+    # columns whose upper and lower halves have different allele frequencies: shard means round differently from the global mean
+    G[:N // 2] = rng.binomial(2, 0.12, size=(N // 2, M)); G[N // 2:] = rng.binomial(2, 0.62, size=(N - N // 2, M))
+    miss = rng.uniform(size=(N, M)) < 0.01
+    miss[:, 5] = False; miss[3, 5] = True                       # a column with a single missing genotype, in the first shard only
+    prefix = str(tmp_path / "gaps")
+    _write_plink(prefix, G, miss)
+    whole = brr.Genotypes.from_bed(prefix, impute_missing=True)
+    want, st_want = whole.unpack(), whole.stats()
+    for world in (2, 3):
+        bounds = sharded.shard_bounds(N, world)
+
+        def fn(r, comm):
+            lo, hi = bounds[r]
+            g = brr.Genotypes.from_bed(prefix, rows=(lo, hi - lo), impute_missing=True)
+            with pytest.raises(brr.BayesRRError):                # not usable before the collective call
+                g.stats()
+            g.shard_stats(comm)
+            out = g.unpack(), g.stats(), g.n_missing
+            g.close()
+            return out
+        res = sharded.ThreadGroup(world).run(fn)
+        got = np.vstack([r[0] for r in res])
+        assert np.array_equal(got, want), "world %d: %d genotypes differ from the unsharded imputation" % (world, int((got != want).sum()))
+        assert sum(r[2] for r in res) == whole.n_missing == int(miss.sum())
+        for r in res:
+            assert rel_inf(r[1]["mean"], st_want["mean"]) < 1e-14 and rel_inf(r[1]["sd"], st_want["sd"]) < 1e-13
+    # the per-shard rule would have given other data: the test is not vacuous
+    lo, hi = sharded.shard_bounds(N, 2)[0]
+    local = G[lo:hi].astype(float); local[miss[lo:hi]] = np.nan
+    shard_fill = np.floor(np.nanmean(local, axis=0) + 0.5)
+    glob = G.astype(float); glob[miss] = np.nan
+    assert np.any(shard_fill != np.floor(np.nanmean(glob, axis=0) + 0.5))
+
+
 # ------------------------------------------------------------------------------------------------ GPU: one process per device
-def _proc_worker(rank, world, port, q):
+PROC_N, PROC_M, PROC_T = 6000, 700, 12
+HS_KW = dict(v0E=1e-3, s02E=1e-3, vL=1.0, vT=1.0, c2=1.0, vC=10.0, sC=10.0)
+
+
+def _proc_case(po, case):
+    """inputs of one process-per-GPU case (every rank and the checking process build the same ones)"""
+    from test_gpu_parity import _groups_case
+    N, M = PROC_N, PROC_M
+    if case == "groups":
+        d, gA, cva, fixed = _groups_case(po, N, M, 3, 2, seed=333)
+        return dict(d=d, gA=gA, cva=cva, fixed=fixed, G=3, F=2)
+    return dict(d=po.synth(N, M, seed=331))
+
+
+def _proc_worker(rank, world, port, q, case):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -212,11 +269,19 @@ def _proc_worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         comm = sharded.torch_comm()
-        N, M, T = 3000, 700, 12
-        d = po.synth(N, M, seed=331)
+        N, M, T = PROC_N, PROC_M, PROC_T
+        cs = _proc_case(po, case)
+        d = cs["d"]
         lo, hi = sharded.shard_bounds(N, world)[rank]
         g = brr.Genotypes.from_packed(pack_codes(d["G"][lo:hi]), hi - lo, device=rank).shard_stats(comm)
-        c = brr.Chain(g, brr.V2, T, seed=332, Y=d["y"][lo:hi], cva=CVA, comm=comm, **HYP)
+        if case == "groups":
+            c = brr.Chain(g, brr.GROUPS, T, seed=332, Y=d["y"][lo:hi], cva=cs["cva"], groups=cs["G"], gAssign=cs["gA"],
+                          fixed=cs["fixed"][lo:hi], comm=comm, **HYP)
+        elif case == "horseshoe":
+            A = (1 / np.sqrt(N)) * (0.1 * M) / (M - 0.1 * M)
+            c = brr.Chain(g, brr.HORSESHOE, T, seed=332, Y=d["y"][lo:hi], A=A, comm=comm, **HS_KW)
+        else:
+            c = brr.Chain(g, brr.V2, T, seed=332, Y=d["y"][lo:hi], cva=CVA, comm=comm, **HYP)
         rows = c.run(T, emit_all=True)
         # device-side check over NCCL that the ranks are bit-identical: max == min of every entry
         t = torch.from_numpy(rows).cuda()
@@ -230,28 +295,49 @@ def _proc_worker(rank, world, port, q):
 
 
 @pytest.mark.gpu
-def test_sharded_v2_one_process_per_gpu(po, brr):
+@pytest.mark.parametrize("case", ["v2", "groups", "horseshoe"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_one_process_per_gpu(po, brr, world, case):
+    """`world` processes, one per GPU, CUDA-IPC exchange windows over NVLink: all ranks bit-identical (checked on the devices
+    over NCCL) and equal to the unsharded oracle (assignments exact, 1e-9); reference src/BayesRv2.cpp:186-245,
+    src/BayesRv2Groups.cpp:216-298, src/HorseshoeR.cpp:219-240"""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (run under gpurun --gpus %d)" % (world, world))
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    ps = [ctx.Process(target=_proc_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + (os.getpid() * 7 + world * 3 + len(case)) % 2000
+    ps = [ctx.Process(target=_proc_worker, args=(r, world, port, q, case)) for r in range(world)]
     for p in ps:
         p.start()
-    res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda x: x[0])
+    res = sorted((q.get(timeout=900) for _ in range(world)), key=lambda x: x[0])
     for p in ps:
         p.join(120)
         assert p.exitcode == 0
     assert all(same for _, same, _ in res), "ranks diverged"
-    N, M, T = 3000, 700, 12
-    d = po.synth(N, M, seed=331)
-    o = po.run_v2(d["X"], d["y"], CVA, T, seed=332, **HYP)
-    a, b = V2Row(res[0][2], N, M), V2Row(o["rows"], N, M)
-    assert np.array_equal(a.comp, b.comp)
-    assert_trace_close("beta", a.beta, b.beta, TOL)
-    assert_trace_close("epsilon", a.eps, b.eps, TOL)
-    assert np.all(np.abs(a.sigmaE / b.sigmaE - 1) <= TOL) and np.all(np.abs(a.sigmaG / b.sigmaG - 1) <= TOL)
+    N, M, T = PROC_N, PROC_M, PROC_T
+    cs = _proc_case(po, case)
+    d = cs["d"]
+    if case == "groups":
+        G, F = cs["G"], cs["F"]
+        o = po.run_groups(d["X"], d["y"], cs["cva"], G, cs["gA"], cs["fixed"], T, seed=332, **HYP)
+        a, b = GroupsRow(res[0][2], N, M, G, F), GroupsRow(o["rows"], N, M, G, F)
+        assert np.array_equal(a.comp, b.comp)
+        for name in ("beta", "eps", "sigmaG", "alpha"):
+            assert_trace_close(name, getattr(a, name), getattr(b, name), TOL)
+        assert rel_inf(a.mu, b.mu) <= TOL and np.all(np.abs(a.sigmaE / b.sigmaE - 1) <= TOL) and np.all(np.abs(a.sigmaF / b.sigmaF - 1) <= TOL)
+    elif case == "horseshoe":
+        A = (1 / np.sqrt(N)) * (0.1 * M) / (M - 0.1 * M)
+        o = po.run_horseshoe(d["X"], d["y"], A, T, seed=332, **HS_KW)
+        a, b = HsRow(res[0][2], N, M), HsRow(o["rows"], N, M)
+        for name in ("beta", "eps", "lam"):
+            assert_trace_close(name, getattr(a, name), getattr(b, name), TOL)
+        assert np.all(np.abs(a.tau / b.tau - 1) <= TOL) and np.all(np.abs(a.sigmaE / b.sigmaE - 1) <= TOL)
+    else:
+        o = po.run_v2(d["X"], d["y"], CVA, T, seed=332, **HYP)
+        a, b = V2Row(res[0][2], N, M), V2Row(o["rows"], N, M)
+        assert np.array_equal(a.comp, b.comp)
+        assert_trace_close("beta", a.beta, b.beta, TOL)
+        assert_trace_close("epsilon", a.eps, b.eps, TOL)
+        assert np.all(np.abs(a.sigmaE / b.sigmaE - 1) <= TOL) and np.all(np.abs(a.sigmaG / b.sigmaG - 1) <= TOL)
