@@ -135,6 +135,22 @@ class Genotypes:
         _check(lib().brr_geno_synthetic(C.c_int64(N), C.c_int64(M), C.c_uint64(seed), C.c_int64(row0), C.c_int(device), C.byref(h)))
         return cls(h)
 
+    def set_dense_columns(self, cols, values):
+        """make the markers `cols` (ascending) dense fp64 columns holding `values` (N x len(cols), taken as given): continuous
+        covariates beside packed genotypes"""
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        values = _f64(values, fortran=True)
+        assert values.shape == (self.N, len(cols))
+        _check(lib().brr_geno_set_dense_columns(self._h, cols.ctypes.data_as(_ip), C.c_int64(len(cols)), _p(values)))
+        return self
+
+    def dense_columns(self):
+        """per-marker index of its dense column, or -1 (packed genotype column)"""
+        n = C.c_int64()
+        idx = np.zeros(self.M, dtype=np.int32)
+        _check(lib().brr_geno_dense_columns(self._h, C.byref(n), idx.ctypes.data_as(_ip)))
+        return idx
+
     def shard_stats(self, comm):
         """make the per-SNP statistics those of the whole matrix (collective over `comm`, a sharded.Comm)"""
         _check(lib().brr_geno_shard_stats(self._h, comm.byref()))

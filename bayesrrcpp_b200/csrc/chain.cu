@@ -109,6 +109,8 @@ struct brr_chain {
     DevBuf<double> fin;
     DevBuf<uint64_t> ll;                     // flagged-word hand-over buffers inside the device: [part nW*PS | bcast PS | delta 2*PS+1 | fin 2*nW] slots
     DevBuf<int32_t> d_gAssign, unit0, gram[2];      // block Gram + cross tiles of iterations it (it & 1) and it + 1
+    bool dense = false;                             // the store holds dense fp64 columns: fp64 Gram tiles (gramd), 64-marker blocks
+    DevBuf<double> gramd[2];
     // Gram pipeline: the Gram of iteration it + 1 depends only on that iteration's marker order, so it runs on its own stream,
     // on the SMs the sweep kernel of iteration it leaves free (a persistent grid of gram_ctas CTAs)
     cudaStream_t gstream = nullptr;
@@ -186,12 +188,13 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     int dev = 0, sms = 0;
     BRR_CUDA(cudaGetDevice(&dev));
     BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int kidx = c->kind == BRR_HORSESHOE ? 1 : c->K == 4 ? 2 : c->K == 3 ? 3 : 0;   // sweep-kernel variant
+    const int kidx = c->kind == BRR_HORSESHOE ? 1 : c->dense ? 0 : c->K == 4 ? 2 : c->K == 3 ? 3 : 0;   // sweep-kernel variant
     BRR_REQUIRE(c->kind == BRR_HORSESHOE || (c->K >= 2 && c->K <= KMAX), BRR_E_SIZE,
                 "number of mixture components must be in [2, " + std::to_string(KMAX) + "]");
     const int64_t units = (c->N + 63) / 64;
     int B = want_block ? want_block : 128;
     BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
+    if (c->dense) B = 64;       // fp64 Gram tiles: 128-marker tiles do not fit beside the tables, and one geometry keeps the instantiations few
     // SMs set aside for the Gram kernel of the next iteration, which runs beside the sweep (none when the caller fixes the workers)
     const int gram_sms = want_workers > 0 ? 0 : (sms >= 64 ? (sms * 3 + 8) / 16 : 0);
     int nW = want_workers > 0 ? want_workers : sms - 1 - gram_sms;
@@ -203,12 +206,12 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         BRR_REQUIRE(TW != 0, BRR_E_SIZE, "more than 2048 rows per worker CTA (" + std::to_string(maxu * 64) +
                     "): shard the individuals over more devices");
         const int seg = (int)maxu * 16;
-        const size_t smem = sweep_smem_bytes(kidx, B, TW, c->K, c->G, (int)c->F, seg);
+        const size_t smem = sweep_smem_bytes(kidx, B, TW, c->K, c->G, (int)c->F, seg, c->dense);
         if (smem > 227 * 1024) {
-            BRR_REQUIRE(B > 32, BRR_E_SIZE, "sweep kernel does not fit shared memory (reduce K or groups)");
+            BRR_REQUIRE(B > 32 && !c->dense, BRR_E_SIZE, "sweep kernel does not fit shared memory (reduce K or groups)");
             B /= 2; continue;
         }
-        const int cores = sweep_max_coresident(kidx, B, TW, smem);
+        const int cores = sweep_max_coresident(kidx, B, TW, smem, c->dense);
         BRR_REQUIRE(cores >= 2, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
         if (nW + 1 > cores) { nW = cores - 1; continue; }
         c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->smem = smem;
@@ -233,7 +236,7 @@ void chain_init(brr_chain *c)
         const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
         const size_t tab = (size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F);
         const size_t ll_words = (2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2;
-        const size_t dev_bytes = 2 * gram_ints * 4 + tab + PERM_RING * pn * 4 + 8 * (size_t)M * 8 + (size_t)N * F * 8 + ll_words * 8 +
+        const size_t dev_bytes = 2 * gram_ints * 4 + (c->dense ? 2 * gram_ints * 8 : 0) + tab + PERM_RING * pn * 4 + 8 * (size_t)M * 8 + (size_t)N * F * 8 + ll_words * 8 +
                                  ((size_t)G * (K + 2) * 3 + (size_t)F * (F + 3)) * 8 + 64 * 256 + ((size_t)1 << 16);
         const size_t pin_bytes = PERM_RING * pn * 4 + ROW_RING * ((size_t)c->row_len() + sizeof(IterScalars) / 8 + 1 + (size_t)G) * 8 + 24 * 256;
         if (!c->dev_arena.base) { BRR_CUDA(cudaMalloc(&c->dev_arena.base, dev_bytes)); c->dev_arena.cap = dev_bytes; }
@@ -332,6 +335,7 @@ void chain_init(brr_chain *c)
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
     for (auto &gb : c->gram) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
+    if (c->dense) for (auto &gb : c->gramd) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     tr.mark("device buffers (hand-over words, Gram x2, tables)");
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
@@ -429,7 +433,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
     const bool sharded = c->win.R > 1;
     if (sharded) { double token = 1.0; comm_allreduce(c->comm, &token, 1); }    // ranks enter the launch sequence together
     const int64_t M = c->M, F = c->F; const int K = c->K, G = c->G;
-    const int kk = c->kind == BRR_HORSESHOE ? 1 : K == 4 ? 2 : K == 3 ? 3 : 0;   // sweep-kernel variant
+    const int kk = c->kind == BRR_HORSESHOE ? 1 : c->dense ? 0 : K == 4 ? 2 : K == 3 ? 3 : 0;   // sweep-kernel variant
     int64_t launches = 0;
     c->prof.zero(c->stream);
     while (c->kev.size() < (size_t)4 * KEV_RING) { cudaEvent_t e; BRR_CUDA(cudaEventCreate(&e)); c->kev.push_back(e); }
@@ -464,10 +468,17 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         if (F > 0) BRR_CUDA(cudaMemcpyAsync(c->d_perm[slot].p + fo, hp + fo, (size_t)F * 4, cudaMemcpyHostToDevice, c->gstream));
         c->perm_used[slot] = true;
         BRR_CUDA(cudaEventRecord(c->ev_gram0[gb], c->gstream));
-        if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
+        if (c->dense) {   // exact int32 counts of the packed pairs, then the fp64 tiles (pairs with a dense column: fp64 dots)
+            int32_t *gi = c->gram[gb].p;
+            launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, gi, gi + self_ints, c->gstream, c->gram_ctas, c->abort_flag.p);
+            double *out = sharded ? reinterpret_cast<double *>(c->win.gram(c->win.rank, gb)) : c->gramd[gb].p;
+            launch_gram_dense(c->g, c->d_perm[slot].p, M, c->B, gi, gi + self_ints, out, out + self_ints, c->gstream, c->gram_ctas);
+            ++launches;
+            if (sharded) { launch_gram_allsum(c->win, gb, (uint32_t)j + 1u, c->gramd[gb].p, all_ints, true, c->abort_flag.p, c->gstream, c->gram_ctas); ++launches; }
+        } else if (sharded) {   // partial Gram over this rank's rows into the window, then the exact sum over all ranks (peer reads)
             int32_t *part = c->win.gram(c->win.rank, gb);
             launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, part, part + self_ints, c->gstream, c->gram_ctas, c->abort_flag.p);
-            launch_gram_allsum(c->win, gb, (uint32_t)j + 1u, c->gram[gb].p, all_ints, c->abort_flag.p, c->gstream, c->gram_ctas);
+            launch_gram_allsum(c->win, gb, (uint32_t)j + 1u, c->gram[gb].p, all_ints, false, c->abort_flag.p, c->gstream, c->gram_ctas);
             ++launches;
         } else launch_gram(c->g, c->d_perm[slot].p, M, c->B, c->gram_impl, c->gram[gb].p, c->gram[gb].p + self_ints, c->gstream, c->gram_ctas, c->abort_flag.p);
         BRR_CUDA(cudaEventRecord(c->ev_gram1[gb], c->gstream));
@@ -504,6 +515,10 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         p.ll_part = c->ll.p; p.ll_bcast = p.ll_part + 2 * (size_t)c->nW * c->PS * 2; p.ll_delta = p.ll_bcast + (3 * (size_t)c->PS + 1) * 2;
         p.ll_fin = p.ll_delta + 2 * (size_t)c->PS * 2;
         p.xgram = c->gram[gb].p + self_ints;
+        if (c->dense) {
+            p.gramd = c->gramd[gb].p; p.xgramd = c->gramd[gb].p + self_ints;
+            p.dense = g->d_dense; p.denseIdx = g->d_dense_idx; p.Npad = g->Npad;
+        }
         p.abort_flag = c->abort_flag.p; p.prof = c->prof.p; p.fin = c->fin.p;
         p.rank = c->win.rank; p.R = c->win.R;
         for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
@@ -598,6 +613,7 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         SetupTrace tr("chain_create");
         std::unique_ptr<brr_chain> c(new brr_chain());
         c->g = g; c->device = g->device; c->kind = cfg->kind; c->N = g->N; c->M = g->M;
+        c->dense = g->Md > 0;
         if (comm) c->comm = *comm;
         c->seed = cfg->seed; c->key = PhiloxKey{ (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32) };
         c->max_iterations = cfg->max_iterations; c->burn_in = cfg->burn_in; c->thinning = cfg->thinning;
@@ -655,10 +671,11 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
             const int kidx = c->kind == BRR_HORSESHOE ? 1 : 0;
             preload_tables(kidx); preload_gram(c->B, c->gram_impl); preload_hyper(c->kind);
             if (R > 1) preload_allsum();
+            if (c->dense) preload_gram_dense();
         }
         tr.mark("kernel preload");
         c->win.rank = c->comm.rank; c->win.R = R;
-        c->win.layout(c->PS, c->nb, c->B, g->Npad);
+        c->win.layout(c->PS, c->nb, c->B, g->Npad, c->dense ? 8 : 4);
         c->win.allocate();
         c->win.connect(c->comm, g->device, g->N, c->B, c->kind, c->M);
         c->N_total = c->win.n_total;

@@ -76,6 +76,9 @@ constexpr int ROW_PAD = 512;   // rows per column are padded to a multiple of th
 }  // namespace brr
 
 // Genotype store (one device).  x[i, j] = a[j] + d[j] * code[i, j], code in {0,1,2}, 2 bits each, column-major.
+// Columns that are not genotype-like (continuous covariates: the "methylation" group of vignettes/BayesRR.Rmd:47-57,150-167) are
+// kept as dense fp64 columns beside the packed matrix: such a column j has dense_idx[j] >= 0, all-zero codes,
+// a = 0, d = 1, and "code" stands for the value itself in every formula (S = sum x, Q = sum x^2).
 struct brr_geno {
     int device = 0;
     int64_t N = 0, M = 0;          // local rows, markers
@@ -85,6 +88,10 @@ struct brr_geno {
     double *d_a = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Q = nullptr, *d_xsq = nullptr, *d_csum = nullptr;
     std::vector<double> h_a, h_d, h_S, h_Q, h_xsq;
     double n_total = 0;            // rows the statistics refer to (== N unless sharded)
+    int64_t Md = 0;                // dense fp64 columns
+    double *d_dense = nullptr;     // Npad x Md, column-major, padding rows 0
+    int32_t *d_dense_idx = nullptr;   // M entries: index of the marker's dense column, or -1 (null when Md == 0)
+    std::vector<int32_t> h_dense_idx;
     // A row shard of a .bed file with missing genotypes to impute: the fill value of a column is the rounded mean over the observed
     // genotypes of ALL ranks, so the codes 3 stay in place (and the statistics undefined) until brr_geno_shard_stats has summed
     // the per-column counts n0, n1, n2, n_missing (4 per marker) over the ranks.

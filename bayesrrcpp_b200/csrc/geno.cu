@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(const double *__restric
                                                          uint8_t *__restrict__ packed, int64_t stride,
                                                          double *__restrict__ a_out, double *__restrict__ d_out,
                                                          double *__restrict__ S_out, double *__restrict__ Q_out,
-                                                         int *__restrict__ bad)
+                                                         int *__restrict__ not_geno /* per column: 1 = not of the form a + d * code */)
 {
     __shared__ double s_lo[8], s_hi[8];
     __shared__ unsigned long long s_n1, s_n2;
@@ -116,7 +116,30 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(const double *__restric
         d_out[col] = hi > lo ? (three ? 0.5 * (hi - lo) : (hi - lo)) : 0.0;
         S_out[col] = c1 + 2.0 * c2;
         Q_out[col] = c1 + 4.0 * c2;
-        if (s_bad) atomicAdd(bad, 1);
+        not_geno[col] = s_bad;
+    }
+}
+
+// Dense (continuous) columns, SURVEY.md 8f-n4: S = sum x, Q = sum x^2 in a fixed order (thread-strided sums, then a fixed tree);
+// a = 0, d = 1 so that x = a + d * "code" holds with the value itself as the code.  One CTA per dense column.
+__global__ void __launch_bounds__(256) dense_stats_kernel(const double *__restrict__ dense, int64_t Npad, int64_t N,
+                                                          const int32_t *__restrict__ cols /* marker of every dense column */,
+                                                          double *__restrict__ a, double *__restrict__ d,
+                                                          double *__restrict__ S, double *__restrict__ Q)
+{
+    __shared__ double s1[8], s2[8];
+    const double *x = dense + (int64_t)blockIdx.x * Npad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double u = 0.0, v = 0.0;
+    for (int64_t i = tid; i < N; i += 256) { const double t = x[i]; u += t; v = fma(t, t, v); }
+    for (int o = 16; o; o >>= 1) { u += __shfl_xor_sync(0xffffffffu, u, o); v += __shfl_xor_sync(0xffffffffu, v, o); }
+    if (lane == 0) { s1[warp] = u; s2[warp] = v; }
+    __syncthreads();
+    if (tid == 0) {
+        double A = 0.0, B = 0.0;
+        for (int w = 0; w < 8; ++w) { A += s1[w]; B += s2[w]; }
+        const int m = cols[blockIdx.x];
+        S[m] = A; Q[m] = B; a[m] = 0.0; d[m] = 1.0;
     }
 }
 
@@ -154,10 +177,11 @@ __global__ void __launch_bounds__(256) stats_packed_kernel(uint8_t *__restrict__
 // a = -mean/sd, d = 1/sd from the code statistics (sd with the N-1 denominator, R scale()); optional overrides.
 __global__ void affine_from_stats_kernel(int64_t M, double n, const double *__restrict__ S, const double *__restrict__ Q,
                                          const double *__restrict__ mean_in, const double *__restrict__ sd_in,
-                                         double *__restrict__ a, double *__restrict__ d)
+                                         double *__restrict__ a, double *__restrict__ d, const int32_t *__restrict__ dense_idx)
 {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= M) return;
+    if (dense_idx && dense_idx[j] >= 0) { a[j] = 0.0; d[j] = 1.0; return; }   // a dense column is taken as given (the caller scaled it)
     const double mean = mean_in ? mean_in[j] : S[j] / n;
     double sd = sd_in ? sd_in[j] : sqrt(fmax(0.0, (Q[j] - S[j] * S[j] / n) / (n - 1.0)));
     if (!(sd > 0.0)) { a[j] = 0.0; d[j] = 0.0; return; }   // monomorphic column: x = 0
@@ -202,7 +226,8 @@ __global__ void synth_kernel(uint8_t *__restrict__ packed, int64_t stride, int64
 // y = X b over the non-zero entries of b: thread = 16-row word, coalesced across threads for each column.
 __global__ void matvec_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t N, int nnz,
                               const int32_t *__restrict__ cols, const double *__restrict__ vals,
-                              const double *__restrict__ a, const double *__restrict__ d, double *__restrict__ y)
+                              const double *__restrict__ a, const double *__restrict__ d, double *__restrict__ y,
+                              const double *__restrict__ dense, const int32_t *__restrict__ dense_idx, int64_t Npad)
 {
     const int64_t wi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (wi * 16 >= N) return;
@@ -211,6 +236,13 @@ __global__ void matvec_kernel(const uint8_t *__restrict__ packed, int64_t stride
     for (int q = 0; q < 16; ++q) acc[q] = 0.0;
     for (int e = 0; e < nnz; ++e) {
         const int64_t col = cols[e];
+        if (dense_idx && dense_idx[col] >= 0) {
+            const double *x = dense + (int64_t)dense_idx[col] * Npad + wi * 16;
+            const double b = vals[e];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) acc[q] += b * x[q];
+            continue;
+        }
         const uint32_t w = reinterpret_cast<const uint32_t *>(packed + col * stride)[wi];
         const double b = vals[e], aa = a[col] * b, dd = d[col] * b;
 #pragma unroll
@@ -225,11 +257,20 @@ __global__ void matvec_kernel(const uint8_t *__restrict__ packed, int64_t stride
 __global__ void __launch_bounds__(256) xt_eps_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t N, int64_t M,
                                                       const double *__restrict__ eps, double eps_sum,
                                                       const double *__restrict__ a, const double *__restrict__ d,
-                                                      double *__restrict__ r)
+                                                      double *__restrict__ r,
+                                                      const double *__restrict__ dense, const int32_t *__restrict__ dense_idx, int64_t Npad)
 {
     const int64_t col = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (col >= M) return;
     const int lane = threadIdx.x & 31;
+    if (dense_idx && dense_idx[col] >= 0) {
+        const double *x = dense + (int64_t)dense_idx[col] * Npad;
+        double s = 0.0;
+        for (int64_t i = lane; i < N; i += 32) s = fma(x[i], eps[i], s);
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) r[col] = s;
+        return;
+    }
     const uint4 *p = reinterpret_cast<const uint4 *>(packed + col * stride);
     const int64_t nv = (N + 63) / 64;
     double s = 0.0;
@@ -267,7 +308,7 @@ void geno_finalize_stats(brr_geno *g)
 void geno_affine_from_stats(brr_geno *g)
 {
     const int64_t M = g->M;
-    affine_from_stats_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, g->n_total, g->d_S, g->d_Q, nullptr, nullptr, g->d_a, g->d_d);
+    affine_from_stats_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, g->n_total, g->d_S, g->d_Q, nullptr, nullptr, g->d_a, g->d_d, g->d_dense_idx);
     BRR_CUDA(cudaGetLastError());
     geno_finalize_stats(g);
 }
@@ -300,9 +341,39 @@ extern "C" void brr_geno_free(brr_geno *g)
 {
     if (!g) return;
     cudaSetDevice(g->device);
-    cudaFree(g->d_packed);
+    cudaFree(g->d_packed); cudaFree(g->d_dense); cudaFree(g->d_dense_idx);
     for (double *p : { g->d_a, g->d_d, g->d_S, g->d_Q, g->d_xsq, g->d_csum }) cudaFree(p);
     delete g;
+}
+
+// Make the markers `cols` (ascending, distinct) of the store dense fp64 columns holding `values` (host, N x n column-major with
+// leading dimension ld): their packed codes are cleared, a = 0, d = 1, S / Q from the values.  Replaces earlier dense columns.
+static void geno_set_dense(brr_geno *g, const std::vector<int32_t> &cols, const double *values, int64_t ld)
+{
+    const int64_t M = g->M, N = g->N, n = (int64_t)cols.size();
+    cudaFree(g->d_dense); cudaFree(g->d_dense_idx); g->d_dense = nullptr; g->d_dense_idx = nullptr; g->Md = 0;
+    g->h_dense_idx.assign((size_t)M, -1);
+    if (n == 0) return;
+    int32_t *d_cols = nullptr;
+    try {
+        for (int64_t k = 0; k < n; ++k) {
+            BRR_REQUIRE(cols[k] >= 0 && cols[k] < M && (k == 0 || cols[k] > cols[k - 1]), BRR_E_ARG, "dense column list must be ascending, distinct and inside [0, M)");
+            g->h_dense_idx[cols[k]] = (int32_t)k;
+        }
+        BRR_CUDA(cudaMalloc(&g->d_dense, (size_t)g->Npad * n * 8));
+        BRR_CUDA(cudaMemset(g->d_dense, 0, (size_t)g->Npad * n * 8));
+        BRR_CUDA(cudaMemcpy2D(g->d_dense, (size_t)g->Npad * 8, values, (size_t)ld * 8, (size_t)N * 8, (size_t)n, cudaMemcpyHostToDevice));
+        BRR_CUDA(cudaMalloc(&g->d_dense_idx, (size_t)M * 4));
+        BRR_CUDA(cudaMemcpy(g->d_dense_idx, g->h_dense_idx.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
+        BRR_CUDA(cudaMalloc(&d_cols, (size_t)n * 4));
+        BRR_CUDA(cudaMemcpy(d_cols, cols.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        for (int64_t k = 0; k < n; ++k) BRR_CUDA(cudaMemsetAsync(g->d_packed + (size_t)cols[k] * g->stride, 0, (size_t)g->stride, 0));
+        dense_stats_kernel<<<(unsigned)n, 256>>>(g->d_dense, g->Npad, N, d_cols, g->d_a, g->d_d, g->d_S, g->d_Q);
+        BRR_CUDA(cudaGetLastError());
+        BRR_CUDA(cudaDeviceSynchronize());
+        g->Md = n;
+    } catch (...) { cudaFree(d_cols); throw; }
+    cudaFree(d_cols);
 }
 
 extern "C" int brr_geno_from_dense(const double *X, int64_t N, int64_t M, int device, brr_geno **out)
@@ -310,28 +381,54 @@ extern "C" int brr_geno_from_dense(const double *X, int64_t N, int64_t M, int de
     return guarded([&] {
         BRR_REQUIRE(X && out, BRR_E_ARG, "brr_geno_from_dense: null pointer");
         brr_geno *g = geno_alloc(N, M, device);
-        double *d_chunk = nullptr; int *d_bad = nullptr;
+        double *d_chunk = nullptr; int *d_flag = nullptr;
         try {
             const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t)256 << 20) / (8 * N)));
             BRR_CUDA(cudaMalloc(&d_chunk, (size_t)chunk * N * 8));
-            BRR_CUDA(cudaMalloc(&d_bad, sizeof(int)));
-            BRR_CUDA(cudaMemset(d_bad, 0, sizeof(int)));
+            BRR_CUDA(cudaMalloc(&d_flag, (size_t)M * sizeof(int)));
             for (int64_t c0 = 0; c0 < M; c0 += chunk) {
                 const int64_t nc = std::min(chunk, M - c0);
                 BRR_CUDA(cudaMemcpy(d_chunk, X + c0 * N, (size_t)nc * N * 8, cudaMemcpyHostToDevice));
                 pack_dense_kernel<<<(unsigned)nc, 256>>>(d_chunk, N, N, g->d_packed + c0 * g->stride, g->stride,
-                                                          g->d_a + c0, g->d_d + c0, g->d_S + c0, g->d_Q + c0, d_bad);
+                                                          g->d_a + c0, g->d_d + c0, g->d_S + c0, g->d_Q + c0, d_flag + c0);
                 BRR_CUDA(cudaGetLastError());
             }
-            int bad = 0;
-            BRR_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
-            BRR_REQUIRE(bad == 0, BRR_E_GENO,
-                        std::to_string(bad) + " column(s) of X are not of the form a + d*code with code in {0,1,2} "
-                        "(dense covariate columns are outside this build's genotype path)");
+            // Columns that are not a + d * code with code in {0,1,2} -- continuous covariates, as the reference's Eigen::MatrixXd X
+            // admits (vignettes/BayesRR.Rmd:150-167 binds scale()d methylation probes to the genotypes) -- stay dense fp64.
+            std::vector<int> flag((size_t)M);
+            BRR_CUDA(cudaMemcpy(flag.data(), d_flag, (size_t)M * sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<int32_t> dense_cols;
+            for (int64_t j = 0; j < M; ++j) if (flag[j]) dense_cols.push_back((int32_t)j);
+            if (!dense_cols.empty()) {
+                // gather the dense columns on the host side by side (they are scattered in X), then one strided upload
+                std::vector<double> vals((size_t)N * dense_cols.size());
+                for (size_t k = 0; k < dense_cols.size(); ++k) memcpy(&vals[k * (size_t)N], X + (size_t)dense_cols[k] * N, (size_t)N * 8);
+                geno_set_dense(g, dense_cols, vals.data(), N);
+            }
             geno_finalize_stats(g);
-        } catch (...) { cudaFree(d_chunk); cudaFree(d_bad); brr_geno_free(g); throw; }
-        cudaFree(d_chunk); cudaFree(d_bad);
+        } catch (...) { cudaFree(d_chunk); cudaFree(d_flag); brr_geno_free(g); throw; }
+        cudaFree(d_chunk); cudaFree(d_flag);
         *out = g;
+    });
+}
+
+extern "C" int brr_geno_set_dense_columns(brr_geno *g, const int32_t *cols, int64_t n_cols, const double *values)
+{
+    return guarded([&] {
+        BRR_REQUIRE(g && (n_cols == 0 || (cols && values)) && n_cols >= 0, BRR_E_ARG, "brr_geno_set_dense_columns: bad arguments");
+        BRR_REQUIRE(!g->pending_impute, BRR_E_ARG, "a .bed row shard with missing genotypes needs brr_geno_shard_stats first");
+        BRR_CUDA(cudaSetDevice(g->device));
+        geno_set_dense(g, std::vector<int32_t>(cols, cols + n_cols), values, g->N);
+        geno_finalize_stats(g);
+    });
+}
+
+extern "C" int brr_geno_dense_columns(const brr_geno *g, int64_t *n_dense, int32_t *dense_idx)
+{
+    return guarded([&] {
+        BRR_REQUIRE(g, BRR_E_ARG, "null genotype store");
+        if (n_dense) *n_dense = g->Md;
+        if (dense_idx) for (int64_t j = 0; j < g->M; ++j) dense_idx[j] = g->Md ? g->h_dense_idx[j] : -1;
     });
 }
 
@@ -349,7 +446,7 @@ static void stats_from_codes(brr_geno *g, const double *mean, const double *sd)
         BRR_REQUIRE(bad == 0, BRR_E_GENO, std::to_string(bad) + " column(s) contain code 3 (missing genotypes are not supported)");
         if (mean) { BRR_CUDA(cudaMalloc(&d_mean, M * 8)); BRR_CUDA(cudaMemcpy(d_mean, mean, M * 8, cudaMemcpyHostToDevice)); }
         if (sd) { BRR_CUDA(cudaMalloc(&d_sd, M * 8)); BRR_CUDA(cudaMemcpy(d_sd, sd, M * 8, cudaMemcpyHostToDevice)); }
-        affine_from_stats_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, g->n_total, g->d_S, g->d_Q, d_mean, d_sd, g->d_a, g->d_d);
+        affine_from_stats_kernel<<<(unsigned)((M + 255) / 256), 256>>>(M, g->n_total, g->d_S, g->d_Q, d_mean, d_sd, g->d_a, g->d_d, g->d_dense_idx);
         BRR_CUDA(cudaGetLastError());
         geno_finalize_stats(g);
     } catch (...) { cudaFree(d_bad); cudaFree(d_mean); cudaFree(d_sd); throw; }
@@ -625,7 +722,7 @@ extern "C" int brr_geno_matvec(const brr_geno *g, const double *b, double *y)
                 BRR_CUDA(cudaMemcpy(d_vals, vals.data(), nnz * 8, cudaMemcpyHostToDevice));
             }
             const int64_t nw = (g->N + 15) / 16;
-            matvec_kernel<<<(unsigned)((nw + 127) / 128), 128>>>(g->d_packed, g->stride, g->N, (int)nnz, d_cols, d_vals, g->d_a, g->d_d, d_y);
+            matvec_kernel<<<(unsigned)((nw + 127) / 128), 128>>>(g->d_packed, g->stride, g->N, (int)nnz, d_cols, d_vals, g->d_a, g->d_d, d_y, g->d_dense, g->d_dense_idx, g->Npad);
             BRR_CUDA(cudaGetLastError());
             BRR_CUDA(cudaMemcpy(y, d_y, g->N * 8, cudaMemcpyDeviceToHost));
         } catch (...) { cudaFree(d_cols); cudaFree(d_vals); cudaFree(d_y); throw; }
@@ -646,7 +743,7 @@ extern "C" int brr_xt_eps(const brr_geno *g, const double *eps, double *r, doubl
             double es = 0.0; for (int64_t i = 0; i < g->N; ++i) es += eps[i];
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
             BRR_CUDA(cudaEventRecord(e0));
-            xt_eps_kernel<<<(unsigned)((g->M + 7) / 8), 256>>>(g->d_packed, g->stride, g->N, g->M, d_eps, es, g->d_a, g->d_d, d_r);
+            xt_eps_kernel<<<(unsigned)((g->M + 7) / 8), 256>>>(g->d_packed, g->stride, g->N, g->M, d_eps, es, g->d_a, g->d_d, d_r, g->d_dense, g->d_dense_idx, g->Npad);
             BRR_CUDA(cudaEventRecord(e1));
             BRR_CUDA(cudaGetLastError());
             BRR_CUDA(cudaEventSynchronize(e1));

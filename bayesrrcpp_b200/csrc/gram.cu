@@ -311,6 +311,82 @@ __global__ void __launch_bounds__(256) cross_bits_kernel(const uint8_t *__restri
     }
 }
 
+// ---- Stores with dense fp64 columns (the reference's X is any Eigen::MatrixXd, src/BayesRv2Groups.cpp:75).  The sweep
+// then reads its Gram and cross tiles as fp64: entry (k, j) = sum over the local rows of c_k c_j with c the 2-bit code of a packed
+// column or the value of a dense one.  Pairs of packed columns are the exact int32 counts of the tensor-core kernel, converted;
+// every pair with a dense column is a fp64 dot in a fixed order (lane-strided 16-row words, xor tree), so runs and ranks reproduce
+// it bit for bit.  One CTA per Gibbs block (persistent over blocks); a warp per pair.
+__device__ __forceinline__ void load16(const uint8_t *__restrict__ packed_col, const double *__restrict__ dense_col, int64_t w, double (&out)[16])
+{
+    if (dense_col != nullptr) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(dense_col + w * 16);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const double2 v = x2[q]; out[2 * q] = v.x; out[2 * q + 1] = v.y; }
+    } else {
+        const uint32_t word = reinterpret_cast<const uint32_t *>(packed_col)[w];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) out[q] = (double)((word >> (2 * q)) & 3u);
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(256) gram_dense_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
+                                                         const double *__restrict__ dense, const int32_t *__restrict__ dense_idx,
+                                                         const int32_t *__restrict__ order, int64_t n_order,
+                                                         const int32_t *__restrict__ Gi, const int32_t *__restrict__ Xi,
+                                                         double *__restrict__ Gd, double *__restrict__ Xd)
+{
+    constexpr int LA = lookahead(B), R = B + LA;
+    __shared__ int32_t cols[R], didx[R];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nblocks = (n_order + B - 1) / B, nwords = Npad / 16;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        __syncthreads();
+        if (tid < R) {
+            const int64_t o = tid < B ? blk * B + tid : blk * B - LA + (tid - B);   // rows B.. : tail of the previous block
+            const int32_t m = (o >= 0 && o < n_order && (tid < B || blk > 0)) ? order[o] : -1;
+            cols[tid] = m; didx[tid] = m >= 0 ? dense_idx[m] : -1;
+        }
+        __syncthreads();
+        for (int i = tid; i < B * B; i += 256) Gd[blk * B * B + i] = (double)Gi[blk * B * B + i];
+        for (int i = tid; i < LA * B; i += 256) Xd[blk * LA * B + i] = (double)Xi[blk * LA * B + i];
+        __syncthreads();
+        // pairs (r, j): r any of the R staged markers, j one of the block's own B, at least one of them dense; r < B is the self
+        // tile, of which the upper triangle is computed and mirrored
+        for (int pair = warp; pair < R * B; pair += 8) {
+            const int r = pair / B, j = pair % B;
+            if (cols[r] < 0 || cols[j] < 0 || (didx[r] < 0 && didx[j] < 0) || (r < B && j < r)) continue;
+            const uint8_t *pr = packed + (int64_t)cols[r] * stride, *pj = packed + (int64_t)cols[j] * stride;
+            const double *dr = didx[r] >= 0 ? dense + (int64_t)didx[r] * Npad : nullptr, *dj = didx[j] >= 0 ? dense + (int64_t)didx[j] * Npad : nullptr;
+            double acc = 0.0;
+            for (int64_t w = lane; w < nwords; w += 32) {
+                double a[16], b[16];
+                load16(pr, dr, w, a); load16(pj, dj, w, b);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc = fma(a[q], b[q], acc);
+            }
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                if (r < B) { Gd[(blk * B + r) * B + j] = acc; Gd[(blk * B + j) * B + r] = acc; }
+                else Xd[(blk * LA + (r - B)) * B + j] = acc;
+            }
+        }
+    }
+}
+
+void preload_gram_dense() { preload_kernel(gram_dense_kernel<64>); }
+
+void launch_gram_dense(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, const int32_t *d_Gi, const int32_t *d_Xi,
+                       double *d_Gd, double *d_Xd, cudaStream_t stream, int max_ctas)
+{
+    const int64_t nb = (n_order + B - 1) / B;
+    if (nb == 0) return;
+    BRR_REQUIRE(B == 64, BRR_E_SIZE, "stores with dense columns run 64-marker Gibbs blocks");
+    const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);
+    gram_dense_kernel<64><<<grid, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, g->d_dense, g->d_dense_idx, d_order, n_order, d_Gi, d_Xi, d_Gd, d_Xd);
+    BRR_CUDA(cudaGetLastError());
+}
+
 template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + lookahead(B)) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + lookahead(B)) * 4 + 64; }
 
 void preload_gram(int B, int impl)

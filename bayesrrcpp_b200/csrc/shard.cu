@@ -32,13 +32,13 @@ static uint64_t process_nonce()
     return nonce;
 }
 
-void Window::layout(int PS, int nb, int B, int64_t Npad)
+void Window::layout(int PS, int nb, int B, int64_t Npad, int gram_elem_bytes)
 {
     size_t o = 0;
     off_xred = o; o = align_up(o + (size_t)4 * PS * R * 16, 256);
     off_xfin = o; o = align_up(o + (size_t)R * 2 * 16, 256);
     off_ready = o; o = align_up(o + (size_t)R * 4, 256);
-    gram_bytes = align_up((size_t)nb * B * (B + lookahead(B)) * 4, 256);
+    gram_bytes = align_up((size_t)nb * B * (B + lookahead(B)) * gram_elem_bytes, 256);
     off_gram = o; if (R > 1) o = o + 2 * gram_bytes;
     off_eps = o; o = align_up(o + (size_t)Npad * 8, 256);
     bytes = o;
@@ -101,11 +101,12 @@ struct AllSumParams {
     int rank, R;
     uint32_t epoch;
     uint32_t *ready[MAXR];          // every rank's flag array (R entries): ready[r][s] = last epoch rank s has published to r
-    const int32_t *part[MAXR];      // every rank's partial Gram
-    int32_t *sum; size_t n4;        // int4 elements
+    const int32_t *part[MAXR];      // every rank's partial Gram (fp64 for stores with dense columns)
+    int32_t *sum; size_t n4;        // int4 (fp64: double2) elements
     int *abort_flag;
 };
 
+template <bool F64>
 __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant__ AllSumParams q)
 {
     __shared__ int s_ok;
@@ -130,6 +131,18 @@ __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant_
     __syncthreads();
     if (!s_ok) return;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (F64) {      // partial tiles of a store with dense columns: summed in rank order on every rank (identical bits everywhere)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < q.n4; i += stride) {
+            double2 v[MAXR];
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) if (r < q.R) v[r] = __ldcg(reinterpret_cast<const double2 *>(q.part[r]) + i);
+            double2 acc = v[0];
+#pragma unroll
+            for (int r = 1; r < MAXR; ++r) if (r < q.R) { acc.x += v[r].x; acc.y += v[r].y; }
+            reinterpret_cast<double2 *>(q.sum)[i] = acc;
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < q.n4; i += stride) {
         int4 acc = make_int4(0, 0, 0, 0);
         int4 v[MAXR];
@@ -143,15 +156,16 @@ __global__ void __launch_bounds__(256) gram_allsum_kernel(const __grid_constant_
 
 }  // namespace
 
-void preload_allsum() { preload_kernel(gram_allsum_kernel); }
+void preload_allsum() { preload_kernel(gram_allsum_kernel<false>); preload_kernel(gram_allsum_kernel<true>); }
 
-void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream, int max_ctas)
+void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, void *d_sum, size_t n_elems, bool f64, int *abort_flag, cudaStream_t stream, int max_ctas)
 {
     AllSumParams q; memset(&q, 0, sizeof q);
-    q.rank = w.rank; q.R = w.R; q.epoch = epoch; q.sum = d_sum; q.n4 = n_int32 / 4; q.abort_flag = abort_flag;
+    q.rank = w.rank; q.R = w.R; q.epoch = epoch; q.sum = static_cast<int32_t *>(d_sum); q.n4 = f64 ? n_elems / 2 : n_elems / 4; q.abort_flag = abort_flag;
     for (int r = 0; r < w.R; ++r) { q.ready[r] = w.ready(r); q.part[r] = w.gram(r, buf); }
     const unsigned blocks = (unsigned)std::min<size_t>((q.n4 + 255) / 256, (size_t)(max_ctas > 0 ? max_ctas : 148) * 8);
-    gram_allsum_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(q);
+    if (f64) gram_allsum_kernel<true><<<blocks ? blocks : 1, 256, 0, stream>>>(q);
+    else gram_allsum_kernel<false><<<blocks ? blocks : 1, 256, 0, stream>>>(q);
     BRR_CUDA(cudaGetLastError());
 }
 
@@ -194,7 +208,8 @@ extern "C" int brr_geno_shard_stats(brr_geno *g, const brr_comm *comm)
         BRR_CUDA(cudaMemcpy(buf.data(), g->d_S, M * 8, cudaMemcpyDeviceToHost));
         BRR_CUDA(cudaMemcpy(buf.data() + M, g->d_Q, M * 8, cudaMemcpyDeviceToHost));
         buf[2 * M] = (double)g->N;
-        comm_allreduce(*comm, buf.data(), (int64_t)buf.size());          // integers below 2^53: exact in any order
+        comm_allreduce(*comm, buf.data(), (int64_t)buf.size());          // integers below 2^53: exact in any order (dense columns: fp64 sums,
+                                                                         // identical on every rank by the call-back's contract)
         BRR_CUDA(cudaMemcpy(g->d_S, buf.data(), M * 8, cudaMemcpyHostToDevice));
         BRR_CUDA(cudaMemcpy(g->d_Q, buf.data() + M, M * 8, cudaMemcpyHostToDevice));
         g->n_total = buf[2 * M];

@@ -29,7 +29,7 @@ struct Window {
     int64_t n_rows[MAXR] = {}, row0[MAXR] = {};
     int64_t n_total = 0;
 
-    void layout(int PS, int nb, int B, int64_t Npad);
+    void layout(int PS, int nb, int B, int64_t Npad, int gram_elem_bytes = 4);
     void allocate();
     void connect(const brr_comm &comm, int device, int64_t n_local, int B, int kind, int64_t M);   // collective
     void release();
@@ -43,7 +43,8 @@ struct Window {
 
 // G_sum = sum over ranks of their partial block Grams (exact int32), every rank reading its peers' partials over NVLink.
 // Signals "my partial of iteration `epoch - 1` is complete" to every peer first, then waits for theirs.
-void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, int32_t *d_sum, size_t n_int32, int *abort_flag, cudaStream_t stream, int max_ctas);
+// f64: the partials are fp64 tiles (stores with dense columns), summed in rank order
+void launch_gram_allsum(const Window &w, int buf, uint32_t epoch, void *d_sum, size_t n_elems, bool f64, int *abort_flag, cudaStream_t stream, int max_ctas);
 
 void comm_check(int rc, const char *what);
 void comm_allreduce(const brr_comm &comm, double *buf, int64_t n);

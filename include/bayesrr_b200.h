@@ -29,7 +29,7 @@ enum {
     BRR_E_ITER = 1,     /* max_iterations < burn_in || max_iterations < 1 || burn_in < 1 (src/BayesRv2.cpp:76-80);
                            the output file has been truncated (and, for V2, the header written) like the reference */
     BRR_E_ARG = 2,      /* invalid argument (null pointer, size mismatch, thinning < 1, ...) */
-    BRR_E_GENO = 3,     /* a column of X is not representable as a + d*code with code in {0,1,2} */
+    BRR_E_GENO = 3,     /* packed genotypes hold code 3 / a .bed file holds missing genotypes and imputation was not asked for */
     BRR_E_CUDA = 4,     /* CUDA failure or no sm_100 device: there is no CPU fallback */
     BRR_E_IO = 5,       /* output file cannot be opened / written */
     BRR_E_SIZE = 6      /* problem does not fit this build's limits (K, rows per device) */
@@ -48,8 +48,8 @@ void brr_set_message_handler(brr_message_fn fn, void *ctx);
 
 /* ------------------------------------------------------------------------------------------------
  * The four reference entry points.  X is N x M column-major fp64 (what Rcpp hands over as
- * Eigen::MatrixXd); each column must take at most three equally spaced values (a standardised
- * 0/1/2 genotype column), see brr_geno_from_dense.
+ * Eigen::MatrixXd); genotype-like columns are packed to 2 bits, any other column stays dense fp64
+ * (brr_geno_from_dense).
  * ------------------------------------------------------------------------------------------------ */
 int brr_BayesRSamplerV2(const char *outputFile, int seed, int max_iterations, int burn_in, int thinning,
                         const double *X, int64_t N, int64_t M, const double *Y,
@@ -80,9 +80,17 @@ int brr_HorseshoeR(const char *outputFile, int seed, int max_iterations, int bur
  * ------------------------------------------------------------------------------------------------ */
 typedef struct brr_geno brr_geno;
 
-/* Pack a dense column-major fp64 matrix (host memory).  Fails with BRR_E_GENO when a column has more
- * than three distinct values or they are not equally spaced (relative tolerance 1e-9). */
+/* Ingest a dense column-major fp64 matrix (host memory).  A column with at most three equally spaced values (relative tolerance
+ * 1e-9) -- a genotype column, raw or centred / scaled -- is packed to 2-bit codes; any other column (a continuous covariate, e.g.
+ * the scale()d methylation probes the reference's vignette binds to the genotypes, vignettes/BayesRR.Rmd:150-167) is kept as a
+ * dense fp64 column and takes the same sweep through the same interfaces. */
 int brr_geno_from_dense(const double *X, int64_t N, int64_t M, int device, brr_geno **out);
+/* Turn the markers cols[0..n_cols) (ascending) of a store into dense fp64 columns holding values (host, N x n_cols column-major,
+ * taken as given: centre / scale them beforehand): how a store built from packed codes or a .bed file gets its continuous
+ * covariates, and how the ranks of a row-sharded chain pass their rows of them (before brr_geno_shard_stats). */
+int brr_geno_set_dense_columns(brr_geno *g, const int32_t *cols, int64_t n_cols, const double *values);
+/* number of dense columns; dense_idx (may be NULL, M entries): index of each marker's dense column or -1 */
+int brr_geno_dense_columns(const brr_geno *g, int64_t *n_dense, int32_t *dense_idx);
 /* Adopt host 2-bit codes: column j starts at packed + j*col_stride_bytes, individual i is bits
  * 2*(i%4).. of byte i/4, code 3 is rejected (missing data is not a concept of the reference).
  * mean/sd NULL -> computed from the codes (sd with the N-1 denominator, like R scale()).       */

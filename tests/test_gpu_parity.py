@@ -27,11 +27,13 @@ def test_pack_dense_roundtrip_and_stats(po, brr):
     assert np.array_equal(codes[:, three], d["G"][:, three])
 
 
-def test_pack_rejects_non_genotype_columns(po, brr):
+def test_non_genotype_columns_stay_dense(po, brr):
+    """a column that is not a + d * code is kept as a dense fp64 column (tests/test_gpu_dense.py), not rejected"""
     X = np.random.default_rng(0).normal(size=(64, 4))
-    with pytest.raises(brr.BayesRRError) as e:
-        brr.Genotypes.from_dense(X)
-    assert e.value.code == brr.E_GENO
+    X[:, 2] = np.random.default_rng(1).integers(0, 3, size=64)          # one genotype column among them
+    g = brr.Genotypes.from_dense(X)
+    assert np.array_equal(g.dense_columns() >= 0, [True, True, False, True])
+    assert rel_inf(g.stats()["xsq"], (np.asfortranarray(X) ** 2).sum(axis=0)) < 1e-13
 
 
 def test_from_packed_matches_dense_and_rejects_missing(po, brr):

@@ -145,7 +145,8 @@ def test_categorical_draw_one_ulp_either_side_of_the_oracle_boundary(po, brr):
     d = po.synth(N, M, seed=460, h2=0.6, causal_frac=0.2)
     t = _first_iteration_tables(po, N, M, seed=461)
     score = np.abs(d["X"].T @ d["y"])
-    for marker in (int(np.argmax(score)), int(np.argsort(score)[M // 2])):     # a marker with a large effect and an ordinary one
+    markers_done = 0
+    for marker in [int(m) for m in np.argsort(-score)[:12]]:                   # markers with visible effects: their boundaries lie inside (0, 1)
         pos = int(np.nonzero(t.perm[0] == marker)[0][0])
 
         def oracle_pick(u):
@@ -162,17 +163,18 @@ def test_categorical_draw_one_ulp_either_side_of_the_oracle_boundary(po, brr):
             c.close(); g.close()
             return int(V2Row(rows, N, M).comp[0, marker]), rows
 
+        u_keep = float(t.mark_u[0, pos])
         lo_pick, hi_pick = oracle_pick(1e-300)[0], oracle_pick(1.0 - 2.0 ** -53)[0]
         checked = 0
         for k in range(lo_pick, hi_pick):                    # boundary between "pick <= k" and "pick > k"
-            lo_b, hi_b = np.float64(1e-300).view(np.int64), np.float64(1.0 - 2.0 ** -53).view(np.int64)
+            lo_b, hi_b = int(np.float64(1e-300).view(np.int64)), int(np.float64(1.0 - 2.0 ** -53).view(np.int64))
             while hi_b - lo_b > 1:                            # positive doubles are ordered like their bit patterns
                 mid = lo_b + (hi_b - lo_b) // 2
                 if oracle_pick(np.int64(mid).view(np.float64))[0] <= k:
                     lo_b = mid
                 else:
                     hi_b = mid
-            b_in, b_out = np.int64(lo_b).view(np.float64), np.int64(hi_b).view(np.float64)   # last u with pick <= k, first with pick > k
+            b_in, b_out = float(np.int64(lo_b).view(np.float64)), float(np.int64(hi_b).view(np.float64))   # last u with pick <= k, first with pick > k
             if not (1e-6 < b_in < 1 - 1e-6):
                 continue                                      # a boundary squeezed against 0 or 1 has no room for the margins
             k_in, k_out = oracle_pick(b_in)[0], oracle_pick(b_out)[0]
@@ -189,4 +191,8 @@ def test_categorical_draw_one_ulp_either_side_of_the_oracle_boundary(po, brr):
                     print("boundary %d|%d of marker %d: at u = %.17g (1 ulp from the oracle's boundary) the GPU picks %d, the oracle %d"
                           % (k_in, k_out, marker, u, got, want))
             checked += 1
-        assert checked >= 1, "no interior boundary found for marker %d" % marker
+        t.mark_u[0, pos] = u_keep
+        markers_done += checked > 0
+        if markers_done >= 2:
+            break
+    assert markers_done >= 2, "fewer than two markers with a boundary inside (1e-6, 1 - 1e-6)"
