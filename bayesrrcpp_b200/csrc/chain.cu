@@ -197,7 +197,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     if (c->dense) B = 64;       // fp64 Gram tiles: 128-marker tiles do not fit beside the tables, and one geometry keeps the instantiations few
     // SMs set aside for the Gram kernel of the next iteration, which runs beside the sweep (none when the caller fixes the workers)
     const int gram_sms = want_workers > 0 ? 0 : (sms >= 64 ? (sms * 3 + 8) / 16 : 0);
-    int nW = want_workers > 0 ? want_workers : sms - 1 - gram_sms;
+    int nW = want_workers > 0 ? want_workers : sms - 1 - SWEEP_REDUCERS - gram_sms;
     nW = (int)std::max<int64_t>(1, std::min<int64_t>(nW, units));
     while (true) {
         const int64_t maxu = (units + nW - 1) / nW;
@@ -213,9 +213,10 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         }
         const int cores = sweep_max_coresident(kidx, B, TW, smem, c->dense);
         BRR_REQUIRE(cores >= 2, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
-        if (nW + 1 > cores) { nW = cores - 1; continue; }
+        BRR_REQUIRE(cores >= 2 + SWEEP_REDUCERS, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
+        if (nW + 1 + SWEEP_REDUCERS > cores) { nW = cores - 1 - SWEEP_REDUCERS; continue; }
         c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->smem = smem;
-        c->gram_ctas = std::max(1, sms - (nW + 1));
+        c->gram_ctas = std::max(1, sms - (nW + 1 + SWEEP_REDUCERS));
         break;
     }
     c->PS = (int)std::max<int64_t>(c->B, c->F);
@@ -523,7 +524,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         p.rank = c->win.rank; p.R = c->win.R;
         for (int q = 0; q < c->win.R; ++q) { p.xred[q] = c->win.xred(q); p.xfin[q] = c->win.xfin(q); }
         p.xphase0 = (uint32_t)((uint64_t)it * (uint64_t)(c->nb + (F > 0 ? 1 : 0)));
-        p.nW = c->nW; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
+        p.nW = c->nW; p.nR = SWEEP_REDUCERS; p.PS = c->PS; p.unit0 = c->unit0.p; p.seg_bytes = c->seg_bytes;
         p.gtab = c->gtab.p;
         launch_tables(kk, c->B, p, c->gtab.p, c->stream);
         launch_sweep(kk, c->B, c->TW, p, c->smem, c->stream);
@@ -680,6 +681,11 @@ static int chain_create_impl(const brr_config *cfg, brr_geno *g, const brr_comm 
         c->win.connect(c->comm, g->device, g->N, c->B, c->kind, c->M);
         c->N_total = c->win.n_total;
         c->d_eps = c->win.eps(c->win.rank);
+        if (c->win.colocated > 1) {   // ranks sharing one device: every rank's sweep and Gram grids must fit on it side by side
+            int sms = 0;
+            BRR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+            c->gram_ctas = std::max(1, (sms - c->win.colocated * (c->nW + 1 + SWEEP_REDUCERS)) / c->win.colocated);
+        }
         tr.mark("exchange window");
         if (R > 1) BRR_REQUIRE((double)c->N_total == g->n_total, BRR_E_ARG,
                                "the genotype store of a sharded chain needs brr_geno_shard_stats first (its statistics must cover all ranks' rows)");

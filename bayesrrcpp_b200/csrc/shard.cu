@@ -61,7 +61,7 @@ void Window::connect(const brr_comm &comm, int device, int64_t n_local, int B, i
     if (R > 1) comm_check(comm.allgather(comm.ctx, &mine, all.data(), (int64_t)sizeof(PeerBlob)), "allgather");
     else all[0] = mine;
     BRR_REQUIRE(all[rank].nonce == mine.nonce && all[rank].base == mine.base, BRR_E_ARG, "brr_comm::allgather did not return this rank's own entry at index `rank`");
-    n_total = 0;
+    n_total = 0; colocated = 1;
     for (int r = 0; r < R; ++r) {
         BRR_REQUIRE(all[r].block == B && all[r].kind == kind && all[r].M == M, BRR_E_ARG,
                     "ranks of a sharded chain disagree on the sampler, the number of markers or the Gibbs block size");
@@ -70,6 +70,7 @@ void Window::connect(const brr_comm &comm, int device, int64_t n_local, int B, i
         // same process (ranks are threads): the address is directly usable.  Decided by a random per-process token, not by the pid
         // alone -- ranks in different PID namespaces (one container per rank) can share a pid; anything else takes the IPC handle
         if (all[r].nonce == mine.nonce && all[r].pid == mine.pid) {
+            if (all[r].device == device) ++colocated;
             if (all[r].device != device) {
                 int can = 0;
                 BRR_CUDA(cudaDeviceCanAccessPeer(&can, device, all[r].device));

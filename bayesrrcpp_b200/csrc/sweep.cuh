@@ -7,6 +7,7 @@ namespace brr {
 constexpr int SWEEP_THREADS = 256;
 constexpr int KMAX = 16;          // mixture components supported by the in-block sampler
 constexpr int MAXR = BRR_MAX_WORLD;   // ranks of a row-sharded chain
+constexpr int SWEEP_REDUCERS = 4;     // reducer CTAs of the sweep kernel: 32 warps, one column total each per chunk of 32 markers
 
 // Scalars of the chain that live on the device between kernels.
 struct IterScalars {
@@ -75,6 +76,7 @@ struct SweepParams {
     int *abort_flag;              // set by the in-kernel watchdog (1: hand-over timed out, 2: bulk copy timed out)
     double *fin;                  // 2: sum eps, sum eps^2 over ALL rows (all ranks), written by the sampler CTA
     int nW; int PS;
+    int nR;                       // reducer CTAs after the workers (column totals of the partial dots)
     const int32_t *unit0;         // nW + 1: first 64-row unit of every worker
     int seg_bytes;                // bytes reserved per staged column segment (max units * 16)
 };
