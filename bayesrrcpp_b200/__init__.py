@@ -337,7 +337,7 @@ class Chain:
         o = np.zeros(16)
         _check(lib().brr_chain_sweep_profile(self._h, _p(o)))
         return dict(gather=o[0], gather_first_chunk=o[1], serial_pass=o[2], publish=o[3], windows=o[4], full_steps=o[5], blocks=o[6],
-                    gather_last_chunk=o[7], worker_wait=o[8], eval_cycles=o[9], resolve_cycles=o[14], prologue_cycles=o[15], worker_dots=o[10], bookkeeping=o[11], chunks_received=o[12], worker_reduce=o[13])
+                    gather_last_chunk=o[7], worker_wait=o[8], eval_cycles=o[9], fp64_draws=o[9], resolve_cycles=o[14], prologue_cycles=o[15], worker_dots=o[10], bookkeeping=o[11], chunks_received=o[12], worker_reduce=o[13])
 
     def geometry(self):
         b, w, r, s = C.c_int(), C.c_int(), C.c_int(), C.c_int()

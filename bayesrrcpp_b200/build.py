@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libbayesrr_b200.so")
 SOURCES = ["geno.cu", "gram.cu", "sweep.cu", "hyper.cu", "shard.cu", "chain.cu", "writer.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = (["-DBRR_ROUND_PROFILE=1"] if os.environ.get("BRR_ROUND_PROFILE") else []) + \
-        (["-DBRR_TENSOR_DOTS=1"] if os.environ.get("BRR_TENSOR_DOTS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        (["-DBRR_TENSOR_DOTS=%s" % os.environ["BRR_TENSOR_DOTS"]] if os.environ.get("BRR_TENSOR_DOTS") else []) + (["-DBRR_DOT_PROFILE=1"] if os.environ.get("BRR_DOT_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "-Xptxas", "-v"]
 
 

@@ -103,7 +103,7 @@ struct brr_chain {
     double mu0 = 0, sigmaE0 = 0;
     int gram_impl = 0;
     // geometry
-    int B = 128, TW = 1, nW = 1, seg_bytes = 16, PS = 128, nb = 0; size_t smem = 0;
+    int B = 128, TW = 1, nW = 1, seg_bytes = 16, rows_per_worker = 64, PS = 128, nb = 0; size_t smem = 0;
     // device state
     DevBuf<double> beta, comp, sigmaG, pi, vcount, betaAcum, d_cva, alpha, d_fixed, fixG, lambda, nu, hs_part;
     DevBuf<double> fin;
@@ -205,7 +205,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         const int TW = words <= 32 ? 1 : words <= 64 ? 2 : words <= 128 ? 4 : 0;
         BRR_REQUIRE(TW != 0, BRR_E_SIZE, "more than 2048 rows per worker CTA (" + std::to_string(maxu * 64) +
                     "): shard the individuals over more devices");
-        const int seg = (int)maxu * 16;
+        const int seg = ((int)maxu | 1) * 16;   // an odd number of 16-byte units per staged column: the unpack's 128-bit reads of consecutive columns are conflict-free
         const size_t smem = sweep_smem_bytes(kidx, B, TW, c->K, c->G, (int)c->F, seg, c->dense);
         if (smem > 227 * 1024) {
             BRR_REQUIRE(B > 32 && !c->dense, BRR_E_SIZE, "sweep kernel does not fit shared memory (reduce K or groups)");
@@ -215,7 +215,7 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
         BRR_REQUIRE(cores >= 2, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
         BRR_REQUIRE(cores >= 2 + SWEEP_REDUCERS, BRR_E_CUDA, "sweep kernel cannot be made co-resident on this device");
         if (nW + 1 + SWEEP_REDUCERS > cores) { nW = cores - 1 - SWEEP_REDUCERS; continue; }
-        c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->smem = smem;
+        c->B = B; c->TW = TW; c->nW = nW; c->seg_bytes = seg; c->rows_per_worker = (int)maxu * 64; c->smem = smem;
         c->gram_ctas = std::max(1, sms - (nW + 1 + SWEEP_REDUCERS));
         break;
     }
@@ -765,12 +765,16 @@ extern "C" int64_t brr_chain_row_len(const brr_chain *c) { return c ? c->row_len
 
 extern "C" int brr_chain_run(brr_chain *c, int n_iter, int emit_all, double *rows, int64_t max_rows, int64_t *n_rows)
 {
-    return guarded([&] {
+    const int rc = guarded([&] {
         BRR_REQUIRE(c && n_iter >= 0, BRR_E_ARG, "bad arguments");
         int64_t produced = 0;
         run_iterations(c, n_iter, emit_all, rows, max_rows, &produced);
         if (n_rows) *n_rows = produced;
     });
+    // A sharded chain that failed keeps its exchange window for the life of the process: its peers may still be running (or have kernels
+    // queued) that store into it, and a freed window would turn one rank's error into an illegal address on every device that maps it.
+    if (rc != BRR_OK && c && c->win.R > 1) c->win.keep_on_release = true;
+    return rc;
 }
 // ---- lossless checkpoint / resume for all four samplers (the reference restarts only the Groups model, from
 // 6-digit CSV text and without its draw state: src/BRv2Grstart.cpp:61-67).  The file holds everything the next iteration reads:
@@ -904,7 +908,7 @@ extern "C" int brr_chain_geometry(const brr_chain *c, int *block, int *workers, 
         BRR_REQUIRE(c, BRR_E_ARG, "null pointer");
         if (block) *block = c->B;
         if (workers) *workers = c->nW;
-        if (rows_per_worker_max) *rows_per_worker_max = c->seg_bytes * 4;
+        if (rows_per_worker_max) *rows_per_worker_max = c->rows_per_worker;
         if (smem_bytes) *smem_bytes = (int)c->smem;
     });
 }

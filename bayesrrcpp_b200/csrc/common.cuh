@@ -54,6 +54,12 @@ template <class K> void preload_kernel(K *kernel)
     BRR_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void *>(kernel)));
 }
 
+// Raise (never lower) a kernel's dynamic shared-memory limit on the current device; cached per (function, device).  A call per launch
+// is not free: the driver may order it against running instances of the function -- and ranks that are threads of one process launch
+// persistent kernels that WAIT for each other, so a rank whose launch sits behind a peer's running kernel times out -- and a smaller
+// value set for one chain must never undercut the larger one another chain of the same geometry needs.
+void ensure_dynamic_smem(const void *fn, size_t bytes);
+
 // BRR_TRACE_SETUP=1: wall-clock milliseconds of the set-up stages on stderr (where the end-to-end time outside the iterations goes)
 struct SetupTrace {
     bool on; const char *what; std::chrono::steady_clock::time_point t;

@@ -3,6 +3,9 @@
 // two deep copies, src/RcppExports.cpp:48-49).  Here X lives in HBM as 2-bit codes, column-major, with a
 // per-marker affine map x = a + d*code, so a standardised column costs N/4 bytes instead of 8N.
 #include "common.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -18,6 +21,19 @@ namespace brr {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
 const char *last_error_cstr() { return g_last_error.c_str(); }
+
+void ensure_dynamic_smem(const void *fn, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> have;
+    int dev = 0;
+    BRR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = have[std::make_pair(fn, dev)];
+    if (bytes <= cur) return;
+    BRR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+}
 
 void require_device(int device)
 {

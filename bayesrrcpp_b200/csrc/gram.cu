@@ -45,6 +45,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *a
         if (clock64() - t0 > 4000000000LL) { if (abort_flag) atomicCAS(abort_flag, 0, 4); break; }
     }
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -163,7 +169,9 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
                 __syncthreads();
                 if (sub == nsub - 1 && L + 2 < nloads) issue_loads(L + 2);      // every thread is past its last read of stage s
-                if (tid == 0) {
+                if (tid == 0) {   // (issuing from an elected lane of a warp-uniform branch makes the eight MMAs leave back to back instead of ~100 cycles
+                                  // apart -- measured SLOWER here, 0.64 instead of 0.575 ms at config 2: the kernel is bound by shared-memory bandwidth,
+                                  // 48 KB of unpack stores + 80 KB of operand reads per 256-row tile, and the spaced-out issue interleaves the two better)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t base = smem_u32(tile);
 #pragma unroll
@@ -414,9 +422,9 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
 #define BRR_GRAM_CASE(BB)                                                                                                   \
     if (B == BB) {                                                                                                          \
         if (impl == 0) {                                                                                                    \
-            /* per device, and ranks may be threads: set on every launch (a cheap host-side call), no cached flag */       \
-            if (d_X) BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
-            else BRR_CUDA(cudaFuncSetAttribute(gram_tc_kernel<BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_tc_smem<BB>())); \
+            /* raised once per device (common.cuh, ensure_dynamic_smem) */       \
+            if (d_X) ensure_dynamic_smem((const void *)gram_tc_kernel<BB, true>, gram_tc_smem<BB>()); \
+            else ensure_dynamic_smem((const void *)gram_tc_kernel<BB, false>, gram_tc_smem<BB>()); \
             const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);                                \
             if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X, abort_flag); \
             else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr, abort_flag); \

@@ -90,6 +90,7 @@ void Window::connect(const brr_comm &comm, int device, int64_t n_local, int B, i
 
 void Window::release()
 {
+    if (keep_on_release) { base = nullptr; return; }      // (the peers' mappings stay open too: their kernels may still be reading this rank's flags)
     for (int r = 0; r < MAXR; ++r) if (ipc_opened[r]) { cudaIpcCloseMemHandle(peer[r]); ipc_opened[r] = false; }
     if (base) cudaFree(base);
     base = nullptr;

@@ -28,6 +28,7 @@ struct Window {
     bool ipc_opened[MAXR] = {};
     int64_t n_rows[MAXR] = {}, row0[MAXR] = {};
     int64_t n_total = 0;
+    bool keep_on_release = false;    // a failed chain leaks its window instead of freeing it (peers may still be writing)
     int colocated = 1;               // ranks of this chain that run on this rank's device (threads of one process: a test configuration)
 
     void layout(int PS, int nb, int B, int64_t Npad, int gram_elem_bytes = 4);

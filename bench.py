@@ -457,6 +457,7 @@ def main():
            "cycles_per_block": {k: prof[k] / nblocks for k in ("gather", "gather_first_chunk", "gather_last_chunk", "serial_pass", "publish", "eval_cycles", "resolve_cycles", "prologue_cycles", "bookkeeping", "chunks_received", "worker_wait", "worker_dots", "worker_reduce")},
            "markers_per_speculative_window": (M * args.steps) / max(prof["windows"], 1),
            "state_changing_marker_fraction": prof["full_steps"] / (M * args.steps),
+           "fp64_draw_fraction": prof["fp64_draws"] / max(prof["full_steps"], 1),
            "young_chain": young,
            "roofline": dict(rooflines[0], peak_source=peak_src,
                             note="serial Gibbs chain: the kernel is latency-bound (M dependent marker steps), see DESIGN.md 3.2"),

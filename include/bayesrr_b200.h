@@ -188,7 +188,7 @@ int brr_chain_last_timing(const brr_chain *c, double *ms, int64_t *launches);
 int brr_chain_kernel_ms(const brr_chain *c, double *gram_sweep_hyper_ms);
 /* SM-clock cycle accounting over the last brr_chain_run (16 values).  Sampler CTA: [0] waiting for the workers' dots ([1] of it for a block's first chunk of 32, [7] for its last),
  * [2] the whole serial in-block pass, [3] block set-up before it, [4] rounds of the walk, [5] state-changing marker steps,
- * [6] blocks, [11] bookkeeping, [12] receiving a block's dots; with -DBRR_ROUND_PROFILE=1 also [9] threshold tests, [14] full
+ * [6] blocks, [11] bookkeeping, [12] receiving a block's dots; [9] draws that took the fp64 evaluation (K = 3, 4); with -DBRR_ROUND_PROFILE=1 instead [9] threshold tests, [14] full
  * draws + corrections, [15] sub-window prologues + waiting for the look-ahead correction (warp 1).  First worker CTA: [8] waiting for / applying deltas, [10] dot stage + send,
  * [13] forming column totals */
 int brr_chain_sweep_profile(const brr_chain *c, double *out16);
