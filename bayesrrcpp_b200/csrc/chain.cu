@@ -196,8 +196,24 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     BRR_REQUIRE(B == 32 || B == 64 || B == 128, BRR_E_ARG, "block must be 32, 64 or 128");
     if (c->dense) B = 64;       // fp64 Gram tiles: 128-marker tiles do not fit beside the tables, and one geometry keeps the instantiations few
     // SMs set aside for the Gram kernel of the next iteration, which runs beside the sweep (none when the caller fixes the workers)
-    const int gram_sms = want_workers > 0 ? 0 : (sms >= 64 ? (sms * 3 + 8) / 16 : 0);
+    // The sweep's pace is set by the sampler CTA and the hand-over latencies, not by the workers' throughput (measured flat from 98 to 124
+    // workers at every BASELINE shape; it grows mildly with the rows per worker), while the Gram kernel is bound by shared-memory
+    // bandwidth per SM: 3.3e-8 ms x markers x local rows / SMs, against 68 ns (mixture) or 110 ns (horseshoe) per marker for the
+    // sweep.  The Gram kernel gets the SMs that keep it at ~85 % of the sweep's time; the workers take the rest, trimmed to the
+    // fewest that reach the same rows per worker, and kept at <= 1024 rows each (TW <= 2: 512-row operand tiles) while that leaves
+    // the Gram kernel at least a ninth of the device.
+    int gram_sms = 0;
+    if (want_workers <= 0 && sms >= 64) {
+        const double per_row = c->kind == BRR_HORSESHOE ? 3.9e-4 : 6.3e-4;
+        gram_sms = (int)std::min<double>(sms / 2, std::max<double>(16.0, std::ceil((double)c->N * per_row)));
+    }
     int nW = want_workers > 0 ? want_workers : sms - 1 - SWEEP_REDUCERS - gram_sms;
+    if (want_workers <= 0 && units > 0) {
+        const int64_t nw_max = std::min<int64_t>(units, nW + 2);
+        int64_t maxu = (units + nw_max - 1) / nw_max;
+        if (maxu > 16 && (units + 15) / 16 <= sms - 1 - SWEEP_REDUCERS - sms / 9) maxu = 16;
+        nW = (int)((units + maxu - 1) / maxu);
+    }
     nW = (int)std::max<int64_t>(1, std::min<int64_t>(nW, units));
     while (true) {
         const int64_t maxu = (units + nW - 1) / nW;
