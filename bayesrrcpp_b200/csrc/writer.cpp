@@ -7,7 +7,10 @@
 // so every kept row reaches the file, in order, for all four samplers.
 #include "common.cuh"
 #include "writer.h"
+#include <algorithm>
 #include <cstdio>
+#include <thread>
+#include <vector>
 #include <cstring>
 #include <charconv>
 #include <cmath>
@@ -83,14 +86,15 @@ std::string sample_header(int kind, int64_t N, int64_t M, int G, int64_t F)
 // "%g" of every value (ostream precision 6, reference src/BayesRv2.cpp:72), joined by ", ".  Rows are long (2M + 4 + N numbers)
 // and mostly zeros and small integers, so those take a short cut; everything else goes through std::to_chars, which is
 // specified to produce what printf("%.6g") produces in the C locale, without the locale / format-string machinery.
-void format_row(const double *row, size_t len, std::string &out)
+// values [0, len) of a span; `lead`: the span continues a row (separator before its first value too)
+static void format_span(const double *row, size_t len, bool lead, std::string &out)
 {
     out.clear();
     out.reserve(len * 12 + 2);
     char t[48];
     for (size_t i = 0; i < len; ++i) {
         const double v = row[i];
-        if (i) out.append(", ", 2);
+        if (i || lead) out.append(", ", 2);
         if (v == 0.0 && !std::signbit(v)) { out.push_back('0'); continue; }
         if (v > 0.0 && v < 100000.0 && v == (double)(int)v) {          // "%g" prints integers below 10^6 as plain digits
             int k = (int)v, n = 0;
@@ -107,6 +111,10 @@ void format_row(const double *row, size_t len, std::string &out)
             out.append(t, (size_t)n);
         }
     }
+}
+void format_row(const double *row, size_t len, std::string &out)
+{
+    format_span(row, len, false, out);
     out.push_back('\n');
 }
 
@@ -123,9 +131,24 @@ void SampleWriter::write_row(const std::vector<double> &row, std::string &text)
 {
     if (binary_) {
         if (fwrite(row.data(), 8, row.size(), f_) != row.size()) io_error_.store(true);
-    } else {
+    } else if (row.size() < (size_t)1 << 16) {
         format_row(row.data(), row.size(), text);
         if (fwrite(text.data(), 1, text.size(), f_) != text.size()) io_error_.store(true);
+    } else {
+        // long rows (a row carries the residual of every individual: 2M + 4 + N numbers) are formatted by several threads, span by
+        // span, and written in order: at 400,000 individuals one thread needs ~7 ms per row and the chain produces one every ~20 ms
+        const size_t hw = std::max(2u, std::thread::hardware_concurrency());
+        const size_t T = std::min<size_t>({ (size_t)8, hw - 1, row.size() >> 15 });
+        const size_t per = (row.size() + T - 1) / T;
+        std::vector<std::string> parts(T);
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < T; ++t)
+            th.emplace_back([&, t] { const size_t lo = t * per, hi = std::min(row.size(), lo + per); if (lo < hi) format_span(row.data() + lo, hi - lo, true, parts[t]); });
+        format_span(row.data(), std::min(per, row.size()), false, parts[0]);
+        for (auto &x : th) x.join();
+        parts[T - 1].push_back('\n');
+        for (size_t t = 0; t < T; ++t)
+            if (fwrite(parts[t].data(), 1, parts[t].size(), f_) != parts[t].size()) io_error_.store(true);
     }
     rows_written_.fetch_add(1);
 }
@@ -192,4 +215,19 @@ extern "C" int64_t brr_format_row(const double *row, int64_t len, char *out, int
     const int64_t n = (int64_t)text.size() - 1;
     if (out && cap > 0) { const int64_t c = n < cap - 1 ? n : cap - 1; memcpy(out, text.data(), (size_t)c); out[c] = 0; }
     return n;
+}
+
+// test hook (CPU only): `nrows` rows through the queue-backed writer of the product -- value 0 of every row replaced by its index --
+// into `path`, CSV text or raw fp64.  Used by tests/test_abi.py (long rows take the multi-threaded formatting path) and by the
+// ThreadSanitizer build of this file (tools/tsan_writer.sh).
+extern "C" int brr_writer_selftest(const char *path, const double *row, int64_t len, int64_t nrows, int binary)
+{
+    if (!path || !row || len < 1 || nrows < 0) return BRR_E_ARG;
+    try {
+        brr::SampleWriter w(path, std::string(), true, binary != 0);
+        std::vector<double> r(row, row + len);
+        for (int64_t i = 0; i < nrows; ++i) { r[0] = (double)i; w.enqueue(r.data(), r.size()); }
+        w.finish();
+        return w.rows_written() == (uint64_t)nrows ? BRR_OK : BRR_E_IO;
+    } catch (const std::exception &) { return BRR_E_IO; }
 }

@@ -412,18 +412,23 @@ def main():
          "frac": gram_ops / (gram_ms * 1e-3) / 1e12 / int8_peak if gram_ms > 0 else None,
          "ms_per_launch": gram_ms, "algorithmic_ops": gram_ops,
          "note": "in situ: a persistent grid on the %d SMs the sweep leaves free, beside the previous iteration's sweep (off the critical path while "
-                 "gram < sweep); the fraction is against the WHOLE device's peak" % max(1, sms - geom["workers"] - 1),
+                 "gram < sweep); the fraction is against the WHOLE device's peak" % max(1, sms - geom["workers"] - 5),
          "stand_alone": None if not gram_alone_ms else {
              "ms": gram_alone_ms, "markers": gram_alone_markers,
              "achieved": 2.0 * (B + LA) * gram_alone_markers * N / (gram_alone_ms * 1e-3) / 1e12,
              "frac": 2.0 * (B + LA) * gram_alone_markers * N / (gram_alone_ms * 1e-3) / 1e12 / int8_peak,
              "note": "the same kernel alone on all SMs (brr_gram_cross_blocks, CUDA events)"}},
-        {"kernel": "sweep_kernel / workers' dot stage (code_b^T eps)", "bound": "fp64 pipe", "unit": "GFMA/s per SM",
-         "peak": fp64_peak / sms / 1e9, "peak_source": "measured here: independent DFMA chains on every SM (brr_peak_fp64), per SM",
-         "achieved": B * rows_w0 / (dots_cycles_per_block / sm_hz) / 1e9 if dots_cycles_per_block > 0 else None,
-         "frac": B * rows_w0 / (dots_cycles_per_block / sm_hz) / (fp64_peak / sms) if dots_cycles_per_block > 0 else None,
-         "note": "first worker CTA: %d markers x %d rows per block in %.0f SM cycles (dots, butterfly, partial sends and the column-total "
-                 "reduction it takes part in), from the kernel's own cycle counters" % (B, rows_w0, dots_cycles_per_block)}]
+        {"kernel": "sweep_kernel / workers' dot stage (code_b^T eps, exact int8 contraction on tcgen05)", "bound": "shared memory",
+         "unit": "B/clk per SM", "peak": 128.0, "peak_source": "B200 shared-memory bandwidth per SM (128 B/clk)",
+         "achieved": 2.25 * B * rows_w0 / dots_cycles_per_block if dots_cycles_per_block > 0 else None,
+         "frac": 2.25 * B * rows_w0 / dots_cycles_per_block / 128.0 if dots_cycles_per_block > 0 else None,
+         "fp64_pipe_equivalent": {
+             "unit": "G genotype-MACs/s per SM", "achieved": B * rows_w0 / (dots_cycles_per_block / sm_hz) / 1e9 if dots_cycles_per_block > 0 else None,
+             "fp64_peak": fp64_peak / sms / 1e9, "frac": B * rows_w0 / (dots_cycles_per_block / sm_hz) / (fp64_peak / sms) if dots_cycles_per_block > 0 else None,
+             "note": "the same stage as fp64 FMAs per genotype (round 1's formulation) against the measured DFMA rate of one SM (brr_peak_fp64)"},
+         "note": "first worker CTA: %d markers x %d rows per block in %.0f SM cycles (residual digits, 2-bit -> int8 unpack, MMAs, TMEM read-out, "
+                 "partial sends), from the kernel's own cycle counters; bytes through shared memory per block = 2.25 x markers x rows (operand tile "
+                 "written once and read once by the tensor core, packed columns read once)" % (B, rows_w0, dots_cycles_per_block)}]
     if args.total_rows:
         wl = "%s N=%d x M=%d synthetic 2-bit genotypes (%s), %d rows per GPU" % (
             {"v2": "BayesRSamplerV2", "groups": "BayesRSamplerV2Groups (22 groups)", "horseshoe": "HorseshoeR"}[args.sampler], N_total, M,

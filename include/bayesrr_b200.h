@@ -252,6 +252,10 @@ int brr_draws_sample(uint64_t seed, int stream, int64_t it, int64_t idx0, int64_
                      double shape, double *out);
 int brr_shuffle_host(uint64_t seed, int stream, int64_t it, int32_t *order, int64_t n);
 
+/* test hook, no device needed: `nrows` copies of `row` (value 0 replaced by the row index) through the product's queue-backed writer into
+ * `path` -- CSV text as brr_format_row gives it, or raw fp64 when `binary` */
+int brr_writer_selftest(const char *path, const double *row, int64_t len, int64_t nrows, int binary);
+
 #ifdef __cplusplus
 }
 #endif
