@@ -468,6 +468,24 @@ def test_grstart_continues_a_groups_chain(po, brr):
     assert rel_inf(c.pi(), o["pi"][-1]) <= TOL
 
 
+def test_grstart_residuals_outgrow_the_digit_scale(po, brr):
+    """the workers cut their residual slice into fixed-point digits against a scale taken at the start of the sweep (2^10 of
+    headroom); a restart from residuals seven orders of magnitude smaller than what the first sweep makes of them (BRV2Grstart takes
+    epsilon and beta independently, src/BRv2Grstart.cpp:61-67) must take a new scale inside the sweep -- never a wrong dot"""
+    N, M, G, T = 1000, 350, 4, 6
+    d, gA, cva, _ = _groups_case(po, N, M, G, 0, seed=71)
+    first = po.run_groups(d["X"], d["y"], cva, G, gA, None, 12, seed=5, **HYP)
+    last = GroupsRow(first["rows"][-1:], N, M, G, 0)
+    st = dict(mu=float(last.mu[0]), beta=last.beta[0], sigmaE=float(last.sigmaE[0]), sigmaGG=last.sigmaG[0],
+              epsilon=last.eps[0] * 1e-7, components=last.comp[0])
+    o = po.run_grstart(st["mu"], st["beta"], st["sigmaE"], st["sigmaGG"], d["X"], st["epsilon"], st["components"],
+                       cva, G, gA, T, seed=6, **HYP)
+    g = brr.Genotypes.from_dense(d["X"])
+    c = brr.Chain(g, brr.GRSTART, T, seed=6, cva=cva, groups=G, gAssign=gA, **st, **HYP)
+    rows = c.run(T, emit_all=True)
+    _compare_groups(o, rows, N, M, G, 0, restart=True)
+
+
 # ------------------------------------------------------------------------------------------------ Horseshoe
 @pytest.mark.parametrize("N,M,block", [(1000, 300, 128), (650, 129, 64)])
 def test_horseshoe_chain_matches_oracle(po, brr, N, M, block):
