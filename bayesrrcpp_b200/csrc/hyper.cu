@@ -27,9 +27,20 @@ __device__ double block_sum(double v, double *scratch)   // deterministic: fixed
 }
 __device__ double strided_sum_sq(const double *x, int64_t n, double *scratch)
 {
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma(x[i], x[i], s);
-    return block_sum(s, scratch);
+    // eight loads in flight per thread: with one, the 400 KB of beta at M = 50,000 cost this single CTA 200 dependent L2 round trips
+    // per thread (~55 of the kernel's 58 us, 1.7 % of a config-2 step)
+    double s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    const int64_t st = blockDim.x;
+    int64_t i = threadIdx.x;
+    for (; i + 7 * st < n; i += 8 * st) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = x[i + u * st];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] = fma(v[u], v[u], s[u]);
+    }
+    for (; i < n; i += st) s[0] = fma(x[i], x[i], s[0]);
+    return block_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])), scratch);
 }
 // 1 / R::rgamma(shape, 1/rate)  (distributions.cpp:27-32; inv_gamma_rng(shape, scale) has the same form, :21-23)
 __device__ __forceinline__ double inv_gamma(double g_unit, double rate) { return 1.0 / ((1.0 / rate) * g_unit); }
@@ -71,7 +82,7 @@ __global__ void __launch_bounds__(256) hyper_mixture_kernel(const HyperParams h)
     double a = 0.0, b = 0.0;
     for (int w = tid; w < h.nW; w += blockDim.x) { a += h.fin[2 * w]; b += h.fin[2 * w + 1]; }
     const double eps_sum = block_sum(a, scratch), eps_sq = block_sum(b, scratch);
-    const double beta_sq = strided_sum_sq(h.beta, h.M, scratch);
+    const double beta_sq = h.kind == BRR_V2 ? strided_sum_sq(h.beta, h.M, scratch) : 0.0;     // (the Groups samplers use the per-group sums of the sweep)
     const double alpha_sq = h.F > 0 ? strided_sum_sq(h.alpha, h.F, scratch) : 0.0;
     const int K = h.K, G = h.G;
     const double N = h.n_total;
