@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbayesrr_b200.so")
+LIB_PATH = os.environ.get("BRR_LIB") or os.path.join(_HERE, "libbayesrr_b200.so")   # BRR_LIB: a variant build of the library (bayesrrcpp_b200/build.py)
 _lib = None
 
 OK, E_ITER, E_ARG, E_GENO, E_CUDA, E_IO, E_SIZE = range(7)
@@ -426,8 +426,12 @@ def read_binary_samples(path):
 
 
 def lookahead(block):
-    """markers of a Gibbs block whose deltas reach the next block through the cross-Gram correction (csrc/common.cuh)"""
-    return 64 if block >= 64 else 32
+    """markers of a Gibbs block whose deltas reach the next block through the cross-Gram correction (csrc/common.cuh; a
+    build-time constant of the library: the whole block by default)"""
+    la = int(lib().brr_lookahead(C.c_int(block)))
+    if la <= 0:
+        raise ValueError("block must be 32, 64 or 128")
+    return la
 
 
 def peak_fp64(device=0):

@@ -7,12 +7,17 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libbayesrr_b200.so")
+# BRR_LIB_SUFFIX=_la64 (with e.g. BRR_LOOKAHEAD128=64): a variant build beside the default one (own object directory, own .so;
+# BRR_LIB=<path> makes the package load it)
+SUFFIX = os.environ.get("BRR_LIB_SUFFIX", "")
+OBJ = os.path.join(HERE, "_build" + SUFFIX)
+LIB = os.path.join(HERE, "libbayesrr_b200%s.so" % SUFFIX)
 SOURCES = ["geno.cu", "gram.cu", "sweep.cu", "hyper.cu", "shard.cu", "chain.cu", "writer.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = (["-DBRR_ROUND_PROFILE=1"] if os.environ.get("BRR_ROUND_PROFILE") else []) + \
-        (["-DBRR_TENSOR_DOTS=%s" % os.environ["BRR_TENSOR_DOTS"]] if os.environ.get("BRR_TENSOR_DOTS") else []) + (["-DBRR_DOT_PROFILE=1"] if os.environ.get("BRR_DOT_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        (["-DBRR_TENSOR_DOTS=%s" % os.environ["BRR_TENSOR_DOTS"]] if os.environ.get("BRR_TENSOR_DOTS") else []) + \
+        (["-DBRR_LOOKAHEAD128=%s" % os.environ["BRR_LOOKAHEAD128"]] if os.environ.get("BRR_LOOKAHEAD128") else []) + \
+        (["-DBRR_PHASE_PROFILE=1"] if os.environ.get("BRR_PHASE_PROFILE") else []) + (["-DBRR_DOT_PROFILE=1"] if os.environ.get("BRR_DOT_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "-Xptxas", "-v"]
 
 

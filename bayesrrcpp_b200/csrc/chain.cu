@@ -198,13 +198,15 @@ void choose_geometry(brr_chain *c, int want_block, int want_workers)
     // SMs set aside for the Gram kernel of the next iteration, which runs beside the sweep (none when the caller fixes the workers)
     // The sweep's pace is set by the sampler CTA and the hand-over latencies, not by the workers' throughput (measured flat from 98 to 124
     // workers at every BASELINE shape; it grows mildly with the rows per worker), while the Gram kernel is bound by shared-memory
-    // bandwidth per SM: 3.3e-8 ms x markers x local rows / SMs, against 68 ns (mixture) or 110 ns (horseshoe) per marker for the
-    // sweep.  The Gram kernel gets the SMs that keep it at ~85 % of the sweep's time; the workers take the rest, trimmed to the
-    // fewest that reach the same rows per worker, and kept at <= 1024 rows each (TW <= 2: 512-row operand tiles) while that leaves
-    // the Gram kernel at least a ninth of the device.
+    // bandwidth per SM: 3.3e-8 ms x markers x local rows / SMs with a 64-marker look-ahead (192 marker rows per operand tile; the
+    // traffic per tile is 576 bytes per marker row + 32 KB for the A operand), against ~62 ns (mixture) or ~100 ns (horseshoe) per
+    // marker for the sweep.  The Gram kernel gets the SMs that keep it at ~85 % of the sweep's time; the workers take the rest,
+    // trimmed to the fewest that reach the same rows per worker, and kept at <= 1024 rows each (TW <= 2: 512-row operand tiles)
+    // while that leaves the Gram kernel at least a ninth of the device.
     int gram_sms = 0;
     if (want_workers <= 0 && sms >= 64) {
-        const double per_row = c->kind == BRR_HORSESHOE ? 3.9e-4 : 6.3e-4;
+        const double la_cost = B == 128 ? (576.0 * (128 + lookahead(128)) + 32768.0) / (576.0 * 192 + 32768.0) : 1.0;
+        const double per_row = (c->kind == BRR_HORSESHOE ? 4.3e-4 : 6.9e-4) * la_cost;
         gram_sms = (int)std::min<double>(sms / 2, std::max<double>(16.0, std::ceil((double)c->N * per_row)));
     }
     int nW = want_workers > 0 ? want_workers : sms - 1 - SWEEP_REDUCERS - gram_sms;
@@ -249,7 +251,7 @@ void chain_init(brr_chain *c)
     BRR_CUDA(cudaSetDevice(c->g->device));
     SetupTrace tr("chain_init");
     {   // one device and one page-locked allocation for everything below (sizes: the large buffers exactly, the rest bounded)
-        const size_t gram_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
+        const size_t gram_ints = (size_t)c->nb * (gram_tile_entries(c->B) + lookahead(c->B) * c->B);
         const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
         const size_t tab = (size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F);
         const size_t ll_words = (2 * (size_t)c->nW * c->PS + (3 * (size_t)c->PS + 1) + 2 * (size_t)c->PS + 2 * (size_t)c->nW) * 2;
@@ -351,8 +353,8 @@ void chain_init(brr_chain *c)
     c->fin.alloc(2); c->fin.zero();
     c->abort_flag.alloc(1); c->abort_flag.zero();
     c->prof.alloc(16); c->prof.zero();
-    for (auto &gb : c->gram) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));      // self tiles, then the look-ahead cross tiles
-    if (c->dense) for (auto &gb : c->gramd) gb.alloc((size_t)c->nb * c->B * (c->B + lookahead(c->B)));
+    for (auto &gb : c->gram) gb.alloc((size_t)c->nb * (gram_tile_entries(c->B) + lookahead(c->B) * c->B));      // self tiles (block-upper trapezoids, common.cuh), then the look-ahead cross tiles
+    if (c->dense) for (auto &gb : c->gramd) gb.alloc((size_t)c->nb * (gram_tile_entries(c->B) + lookahead(c->B) * c->B));
     c->gtab.alloc((size_t)c->nb * sweep_table_bytes(c->kind == BRR_HORSESHOE ? 1 : 0, c->B, K, G, (int)F));
     tr.mark("device buffers (hand-over words, Gram x2, tables)");
     const size_t pn = (size_t)c->nb * c->B + (size_t)std::max<int64_t>(F, 1);
@@ -463,7 +465,7 @@ void run_iterations_body(brr_chain *c, int n_iter, int emit_all, double *rows, i
         }
     };
     BRR_CUDA(cudaEventRecord(c->ev0, c->stream));
-    const size_t self_ints = (size_t)c->nb * c->B * c->B, all_ints = (size_t)c->nb * c->B * (c->B + lookahead(c->B));
+    const size_t self_ints = (size_t)c->nb * gram_tile_entries(c->B), all_ints = self_ints + (size_t)c->nb * lookahead(c->B) * c->B;
     const size_t fo = (size_t)c->nb * c->B;
     // Marker order (host shuffle, reference :182) + block Gram of iteration j, on the Gram stream.  Called once per iteration,
     // in order, one iteration ahead of the sweep.

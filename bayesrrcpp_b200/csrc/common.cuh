@@ -75,7 +75,27 @@ struct SetupTrace {
 
 // Look-ahead depth of the sweep for Gibbs blocks of B markers: the deltas of the last lookahead(B) markers of a block reach the
 // next block through the cross-Gram correction instead of through the workers' dots (sweep.cu, gram.cu).
-__host__ __device__ constexpr int lookahead(int B) { return B >= 64 ? 64 : 32; }
+// 128-marker blocks: the whole block (the workers form the dots of block b + 1 while the sampler walks block b, so the per-block
+// latency loop deltas -> residual update -> dots -> reducer -> (NVLink) -> sampler has a block's time to turn over; with 64 the
+// sampler waited 1.6k cycles per block on one GPU and 5.7k on eight).  -DBRR_LOOKAHEAD128=64|96|128 (env BRR_LOOKAHEAD128 of
+// bayesrrcpp_b200.build).
+#ifndef BRR_LOOKAHEAD128
+#define BRR_LOOKAHEAD128 128
+#endif
+static_assert(BRR_LOOKAHEAD128 == 32 || BRR_LOOKAHEAD128 == 64 || BRR_LOOKAHEAD128 == 96 || BRR_LOOKAHEAD128 == 128, "look-ahead depth of 128-marker blocks");
+__host__ __device__ constexpr int lookahead(int B) { return B >= 128 ? BRR_LOOKAHEAD128 : B >= 64 ? 64 : 32; }
+
+// Layout of a block's self Gram tile (gram.cu -> sweep.cu).  The walk reads row j of the tile only at the columns of j's own
+// 32-marker sub-window and the later ones (the markers not yet visited), so a tile is stored as its block-upper trapezoid: the 32
+// rows of sub-window q, each cut to the B - 32 q columns from 32 q on, one sub-window after the other -- 10,240 of 16,384 entries
+// at B = 128.  One flat bulk copy per block as before, and the sampler's shared memory holds the deeper look-ahead's cross tile.
+__host__ __device__ constexpr int gram_tile_entries(int B) { return 32 * (B * (B / 32) - 16 * (B / 32) * (B / 32 - 1)); }
+__host__ __device__ constexpr int gram_subwindow_offset(int B, int q) { return 32 * q * B - 512 * q * (q - 1); }   // first entry of sub-window q's rows
+// entry (i, j) of a tile, or -1 when it is not stored (j's sub-window precedes i's); the tile is symmetric: (j, i) is stored then
+__host__ __device__ constexpr int gram_tile_index(int B, int i, int j)
+{
+    return j / 32 < i / 32 ? -1 : gram_subwindow_offset(B, i / 32) + (i % 32) * (B - 32 * (i / 32)) + (j - 32 * (i / 32));
+}
 
 constexpr int ROW_PAD = 512;   // rows per column are padded to a multiple of this (codes 0): 128-byte column stride
 

@@ -12,11 +12,11 @@
 namespace brr {
 
 constexpr int GRAM_KC = 256;                       // rows (K) per operand tile (one commit group of MMAs)
-constexpr int GRAM_LDR = 1024;                     // rows per load stage: ONE 256-byte bulk copy per marker (bulk copies have a fixed
-                                                   // issue cost of tens of cycles each; 128-byte copies left the kernel copy-issue bound)
-constexpr int GRAM_LA_MAX = 64;                    // look-ahead markers (lookahead(B) <= 64): the tail of the previous block (cross products)
-constexpr int GRAM_STAGE_ROW = GRAM_LDR / 4 + 16;  // bytes per staged packed column (padded: conflict-free 128-bit reads)
-constexpr int GRAM_TILE_BYTES = (128 + GRAM_LA_MAX) * GRAM_KC;   // int8 operand tile: up to 128 + 64 marker rows x KC
+// rows per load stage: ONE bulk copy per marker and stage (bulk copies have a fixed issue cost of tens of cycles each; 128-byte
+// copies left the kernel copy-issue bound), as many rows as fit beside the two operand tiles of R = B + lookahead(B) marker rows
+__host__ __device__ constexpr int gram_ldr(int R) { return R > 224 ? 512 : R > 192 ? 768 : 1024; }
+__host__ __device__ constexpr int gram_stage_row(int R) { return gram_ldr(R) / 4 + 16; }   // bytes per staged packed column (padded to an odd number of 16-byte units: conflict-free 128-bit reads)
+__host__ __device__ constexpr int gram_tile_bytes(int R) { return (R > 128 ? R : 128) * GRAM_KC; }   // int8 operand tile: R marker rows x KC (the A operand always reads 128: rows >= R stay zero)
 constexpr int GRAM_SBO = (GRAM_KC / 16) * 128;     // byte stride between 8-marker groups
 constexpr int GRAM_LBO = 128;                      // byte stride between K-adjacent 8x16B core matrices
 
@@ -83,8 +83,11 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     static_assert(B == 32 || B == 64 || B == 128, "block size");
     constexpr int LA = lookahead(B);
     constexpr int R = CROSS ? B + LA : B;                   // marker rows of the operand tile
+    static_assert(R <= 256 && R % 16 == 0, "N of the MMA (one accumulator column per marker row of the tile)");
+    constexpr int GRAM_LDR = gram_ldr(R), GRAM_STAGE_ROW = gram_stage_row(R), GRAM_TILE_BYTES = gram_tile_bytes(R);
+    constexpr int TE = gram_tile_entries(B);                // entries of a stored self tile (block-upper trapezoid, common.cuh)
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *tile0 = smem;                                  // 2 x 64 KB operand tiles
+    uint8_t *tile0 = smem;                                  // 2 operand tiles of max(R, 128) x KC bytes
     uint8_t *stage0 = smem + 2 * GRAM_TILE_BYTES;           // 2 x R x GRAM_STAGE_ROW staged packed columns
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage0 + 2 * R * GRAM_STAGE_ROW);   // full[2], free[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
@@ -94,7 +97,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
     uint64_t *full = bars, *freeb = bars + 2;
     const int64_t nblocks = (n_order + B - 1) / B;
 
-    if (warp == 0) {   // TMEM: 128 lanes x 256 int32 columns (B + lookahead used)
+    if (warp == 0) {   // TMEM: 128 lanes x 256 int32 columns (R = B + lookahead(B) <= 256 used)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -135,7 +138,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
             bulk_g2s(stage0 + (s * R + tid) * GRAM_STAGE_ROW, packed + (int64_t)cols[tid] * stride + (int64_t)L * (GRAM_LDR / 4), bytes, &full[s]);
     };
     if (nvalid == 0) {   // nothing to do but keep the protocol simple: write zeros
-        for (int i = tid; i < B * B; i += 256) G[blk * B * B + i] = 0;
+        for (int i = tid; i < TE; i += 256) G[blk * TE + i] = 0;
         if (CROSS) for (int i = tid; i < LA * B; i += 256) X[blk * LA * B + i] = 0;
     } else {
         issue_loads(0);
@@ -194,11 +197,13 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
             if (g > 1) { const int l2 = last - 1; mbar_wait(&freeb[l2 & 1], (uint32_t)((l2 >> 1) & 1), abort_flag); }
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: TMEM lane = marker row i, column = marker j
+        // epilogue: TMEM lane = marker row i, column = marker j.  Of the self tile only the columns of the row's own sub-window and the
+        // later ones are stored (gram_tile_index, common.cuh): warp w holds sub-window w's rows
         if (warp < 4) {
             const int row = warp * 32 + (tid & 31);
 #pragma unroll
             for (int c0 = 0; c0 < B; c0 += 32) {
+                if (c0 < warp * 32) continue;                 // (warp-uniform)
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
                 asm volatile(
@@ -212,7 +217,7 @@ gram_tc_kernel(const uint8_t *__restrict__ packed, int64_t stride, int64_t Npad,
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (row < B) {
-                    int4 *dst = reinterpret_cast<int4 *>(G + (blk * B + row) * B + c0);
+                    int4 *dst = reinterpret_cast<int4 *>(G + blk * TE + gram_tile_index(B, row, c0));
 #pragma unroll
                     for (int q = 0; q < 8; ++q) dst[q] = make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
                 }
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(256) gram_dp4a_kernel(const uint8_t *__restric
 #pragma unroll
         for (int b = 0; b < TS; ++b) {
             const int i = ti + 16 * a, j = tj + 16 * b;
-            if (i < B && j < B) G[(blk * B + i) * B + j] = acc[a][b];
+            if (i < B && j < B && gram_tile_index(B, i, j) >= 0) G[blk * gram_tile_entries(B) + gram_tile_index(B, i, j)] = acc[a][b];
         }
 }
 
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(256) gram_dense_kernel(const uint8_t *__restri
                                                          const int32_t *__restrict__ Gi, const int32_t *__restrict__ Xi,
                                                          double *__restrict__ Gd, double *__restrict__ Xd)
 {
-    constexpr int LA = lookahead(B), R = B + LA;
+    constexpr int LA = lookahead(B), R = B + LA, TE = gram_tile_entries(B);
     __shared__ int32_t cols[R], didx[R];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nblocks = (n_order + B - 1) / B, nwords = Npad / 16;
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(256) gram_dense_kernel(const uint8_t *__restri
             cols[tid] = m; didx[tid] = m >= 0 ? dense_idx[m] : -1;
         }
         __syncthreads();
-        for (int i = tid; i < B * B; i += 256) Gd[blk * B * B + i] = (double)Gi[blk * B * B + i];
+        for (int i = tid; i < TE; i += 256) Gd[blk * TE + i] = (double)Gi[blk * TE + i];
         for (int i = tid; i < LA * B; i += 256) Xd[blk * LA * B + i] = (double)Xi[blk * LA * B + i];
         __syncthreads();
         // pairs (r, j): r any of the R staged markers, j one of the block's own B, at least one of them dense; r < B is the self
@@ -375,7 +380,10 @@ __global__ void __launch_bounds__(256) gram_dense_kernel(const uint8_t *__restri
             }
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) {
-                if (r < B) { Gd[(blk * B + r) * B + j] = acc; Gd[(blk * B + j) * B + r] = acc; }
+                if (r < B) {     // (r, j) with j >= r is always stored; its mirror only inside r's own sub-window
+                    Gd[blk * TE + gram_tile_index(B, r, j)] = acc;
+                    if (gram_tile_index(B, j, r) >= 0) Gd[blk * TE + gram_tile_index(B, j, r)] = acc;
+                }
                 else Xd[(blk * LA + (r - B)) * B + j] = acc;
             }
         }
@@ -395,7 +403,11 @@ void launch_gram_dense(const brr_geno *g, const int32_t *d_order, int64_t n_orde
     BRR_CUDA(cudaGetLastError());
 }
 
-template <int B> static size_t gram_tc_smem() { return 2 * GRAM_TILE_BYTES + 2 * (B + lookahead(B)) * GRAM_STAGE_ROW + 4 * 8 + 8 + (B + lookahead(B)) * 4 + 64; }
+template <int B, bool CROSS> static size_t gram_tc_smem()
+{
+    constexpr int R = CROSS ? B + lookahead(B) : B;
+    return 2 * gram_tile_bytes(R) + 2 * R * gram_stage_row(R) + 4 * 8 + 8 + R * 4 + 64;
+}
 
 void preload_gram(int B, int impl)
 {
@@ -411,7 +423,7 @@ void preload_gram(int B, int impl)
     }
 }
 
-// launch on `stream`; G must hold nblocks * B * B int32
+// launch on `stream`; G must hold nblocks * gram_tile_entries(B) int32 (tiles stored as block-upper trapezoids, common.cuh)
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
                  int max_ctas, int *abort_flag)
 {
@@ -423,11 +435,11 @@ void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int
     if (B == BB) {                                                                                                          \
         if (impl == 0) {                                                                                                    \
             /* raised once per device (common.cuh, ensure_dynamic_smem) */       \
-            if (d_X) ensure_dynamic_smem((const void *)gram_tc_kernel<BB, true>, gram_tc_smem<BB>()); \
-            else ensure_dynamic_smem((const void *)gram_tc_kernel<BB, false>, gram_tc_smem<BB>()); \
+            if (d_X) ensure_dynamic_smem((const void *)gram_tc_kernel<BB, true>, gram_tc_smem<BB, true>()); \
+            else ensure_dynamic_smem((const void *)gram_tc_kernel<BB, false>, gram_tc_smem<BB, false>()); \
             const unsigned grid = (unsigned)(max_ctas > 0 && max_ctas < nb ? max_ctas : nb);                                \
-            if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X, abort_flag); \
-            else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr, abort_flag); \
+            if (d_X) gram_tc_kernel<BB, true><<<grid, 256, gram_tc_smem<BB, true>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, d_X, abort_flag); \
+            else gram_tc_kernel<BB, false><<<grid, 256, gram_tc_smem<BB, false>(), stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G, nullptr, abort_flag); \
         } else {                                                                                                            \
             gram_dp4a_kernel<BB><<<(unsigned)nb, 256, 0, stream>>>(g->d_packed, g->stride, g->Npad, d_order, n_order, d_G);      \
         }                                                                                                                   \
@@ -450,14 +462,17 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
 {
     return guarded([&] {
         BRR_REQUIRE(g && order && G_out && n_order > 0, BRR_E_ARG, "bad arguments");
+        BRR_REQUIRE(block == 32 || block == 64 || block == 128, BRR_E_ARG, "block must be 32, 64 or 128");
         BRR_CUDA(cudaSetDevice(g->device));
         for (int64_t i = 0; i < n_order; ++i)
             BRR_REQUIRE(order[i] >= -1 && order[i] < g->M, BRR_E_ARG, "order entry out of range");
         const int64_t nb = (n_order + block - 1) / block;
         int32_t *d_order = nullptr, *d_G = nullptr, *d_X = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+        const int TE = gram_tile_entries(block);
+        std::vector<int32_t> trimmed((size_t)nb * TE);
         try {
             BRR_CUDA(cudaMalloc(&d_order, n_order * 4));
-            BRR_CUDA(cudaMalloc(&d_G, (size_t)nb * block * block * 4));
+            BRR_CUDA(cudaMalloc(&d_G, (size_t)nb * TE * 4));
             if (X_out) BRR_CUDA(cudaMalloc(&d_X, (size_t)nb * lookahead(block) * block * 4));
             BRR_CUDA(cudaMemcpy(d_order, order, n_order * 4, cudaMemcpyHostToDevice));
             BRR_CUDA(cudaEventCreate(&e0)); BRR_CUDA(cudaEventCreate(&e1));
@@ -467,12 +482,22 @@ extern "C" int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, in
             BRR_CUDA(cudaEventRecord(e1));
             BRR_CUDA(cudaEventSynchronize(e1));
             float t = 0; BRR_CUDA(cudaEventElapsedTime(&t, e0, e1)); if (ms) *ms = t;
-            BRR_CUDA(cudaMemcpy(G_out, d_G, (size_t)nb * block * block * 4, cudaMemcpyDeviceToHost));
+            BRR_CUDA(cudaMemcpy(trimmed.data(), d_G, (size_t)nb * TE * 4, cudaMemcpyDeviceToHost));
             if (X_out) BRR_CUDA(cudaMemcpy(X_out, d_X, (size_t)nb * lookahead(block) * block * 4, cudaMemcpyDeviceToHost));
         } catch (...) { cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); throw; }
         cudaFree(d_order); cudaFree(d_G); cudaFree(d_X); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        // the kernels store a tile as its block-upper trapezoid (common.cuh); the caller gets whole B x B tiles: an entry that is not
+        // stored is its mirror image (the Gram is symmetric)
+        for (int64_t b = 0; b < nb; ++b)
+            for (int i = 0; i < block; ++i)
+                for (int j = 0; j < block; ++j) {
+                    const int idx = gram_tile_index(block, i, j) >= 0 ? gram_tile_index(block, i, j) : gram_tile_index(block, j, i);
+                    G_out[((size_t)b * block + i) * block + j] = trimmed[(size_t)b * TE + idx];
+                }
     });
 }
+
+extern "C" int brr_lookahead(int block) { return block == 32 || block == 64 || block == 128 ? lookahead(block) : 0; }
 
 extern "C" int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
                                int32_t *G_out, double *ms)

@@ -38,7 +38,7 @@ void Window::layout(int PS, int nb, int B, int64_t Npad, int gram_elem_bytes)
     off_xred = o; o = align_up(o + (size_t)4 * PS * R * 16, 256);
     off_xfin = o; o = align_up(o + (size_t)R * 2 * 16, 256);
     off_ready = o; o = align_up(o + (size_t)R * 4, 256);
-    gram_bytes = align_up((size_t)nb * B * (B + lookahead(B)) * gram_elem_bytes, 256);
+    gram_bytes = align_up((size_t)nb * (gram_tile_entries(B) + lookahead(B) * B) * gram_elem_bytes, 256);
     off_gram = o; if (R > 1) o = o + 2 * gram_bytes;
     off_eps = o; o = align_up(o + (size_t)Npad * 8, 256);
     bytes = o;

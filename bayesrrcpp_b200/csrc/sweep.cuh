@@ -29,7 +29,7 @@ struct SweepParams {
     double n_total;
     // iteration inputs
     const int32_t *perm;          // M markers in visiting order
-    const int32_t *gram;          // nb x B x B int32 (codes), rows/cols in visiting order
+    const int32_t *gram;          // nb x gram_tile_entries(B) int32 (codes), rows/cols in visiting order, block-upper trapezoid of every tile (common.cuh)
     const int32_t *xgram;         // nb x lookahead(B) x B int32: products with the last lookahead(B) markers of the previous block
     // stores with dense fp64 columns: the same tiles as fp64 (gram.cu, gram_dense_kernel) and the dense columns
     const double *gramd, *xgramd;
@@ -96,13 +96,13 @@ void preload_allsum();
 size_t sweep_smem_bytes(int kind, int B, int TW, int K, int G, int F, int seg_bytes, bool dense = false);
 int sweep_max_coresident(int kind, int B, int TW, size_t smem, bool dense = false);
 
-// d_G: nb x B x B self products; d_X (nullable): nb x lookahead(B) x B products with the last lookahead(B) markers of the previous block
+// d_G: nb x gram_tile_entries(B) self products (a tile is stored as its block-upper trapezoid, common.cuh); d_X (nullable): nb x lookahead(B) x B products with the last lookahead(B) markers of the previous block
 // max_ctas > 0: persistent grid of at most that many CTAs (the tensor-core kernel loops over the blocks)
 // abort_flag (nullable): the chain's sticky watchdog flag (a lost bulk copy raises code 4)
 void launch_gram(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, int impl, int32_t *d_G, int32_t *d_X, cudaStream_t stream,
                  int max_ctas = 0, int *abort_flag = nullptr);
 // Stores with dense columns: the same tiles as fp64 -- the exact int32 counts of the packed pairs (d_Gi, d_Xi: launch_gram's output) converted,
-// every pair with a dense column as a fp64 dot over the local rows in a fixed order.  d_Gd: nb x B x B, d_Xd: nb x lookahead(B) x B.
+// every pair with a dense column as a fp64 dot over the local rows in a fixed order.  d_Gd: nb x gram_tile_entries(B), d_Xd: nb x lookahead(B) x B.
 void launch_gram_dense(const brr_geno *g, const int32_t *d_order, int64_t n_order, int B, const int32_t *d_Gi, const int32_t *d_Xi,
                        double *d_Gd, double *d_Xd, cudaStream_t stream, int max_ctas = 0);
 void preload_gram_dense();

@@ -238,10 +238,13 @@ int64_t brr_format_row(const double *row, int64_t len, char *out, int64_t cap);
 int brr_gram_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
                     int32_t *G_out, double *ms);
 /* same, plus X[b][jl][k] = sum_n code[n, order[b*B - LA + jl]] * code[n, order[b*B + k]] (int32, nb x LA x B; block 0: zeros),
- * LA = 64 for blocks of 64 or 128 markers, 32 for blocks of 32: the products with the last LA markers of the previous block
- * that the sweep's look-ahead correction uses (X_out may be NULL) */
+ * LA = brr_lookahead(B): the products with the last LA markers of the previous block that the sweep's look-ahead correction
+ * uses (X_out may be NULL) */
 int brr_gram_cross_blocks(const brr_geno *g, const int32_t *order, int64_t n_order, int block, int impl,
                           int32_t *G_out, int32_t *X_out, double *ms);
+/* look-ahead depth of the sweep for Gibbs blocks of `block` markers (the whole block: 128 for 128, 64 for 64, 32 for 32; a build-time constant of the
+ * library): the deltas of a block's last LA markers reach the next block's dots through the cross-Gram correction; 0 = unsupported block */
+int brr_lookahead(int block);
 /* r[j] = sum_n x[n, j] * eps[n] for every marker (host eps N -> host r M), the streaming X^T eps kernel */
 int brr_xt_eps(const brr_geno *g, const double *eps, double *r, double *ms);
 /* measured fp64 FMA throughput of the device (thread-level DFMAs per second, independent chains on every SM): the roofline the

@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -218,3 +220,44 @@ def test_message_handler_is_exported_and_silent_by_default(brr):
     L.brr_set_message_handler(cb, None)
     L.brr_set_message_handler(C.cast(None, FN), None)
     assert got == []
+
+
+def test_gram_tile_layout_is_a_bijection_and_lookahead_is_exported(brr, tmp_path):
+    """csrc/common.cuh: a block's self Gram tile is stored as its block-upper trapezoid.  Every (i, j) whose column sub-window is not
+    before its row's maps to a distinct entry of [0, gram_tile_entries), rows are contiguous from the first column of their own
+    sub-window on (what the sampler's register walk and the kernels' 128-bit stores assume), everything else maps to -1 while its mirror
+    image is stored; the look-ahead depths the library reports are legal (multiples of 32, at most the block)."""
+    import subprocess
+    src = tmp_path / "layout.cu"
+    src.write_text(r'''
+#include "%s/bayesrrcpp_b200/csrc/common.cuh"
+#include <cstdio>
+#include <vector>
+int main()
+{
+    for (int B : {32, 64, 128}) {
+        const int TE = brr::gram_tile_entries(B);
+        std::vector<int> seen(TE, 0);
+        for (int i = 0; i < B; ++i)
+            for (int j = 0; j < B; ++j) {
+                const int idx = brr::gram_tile_index(B, i, j);
+                if (j / 32 < i / 32) { if (idx != -1 || brr::gram_tile_index(B, j, i) < 0) { printf("mirror %%d %%d %%d\n", B, i, j); return 1; } continue; }
+                if (idx < 0 || idx >= TE || seen[idx]++) { printf("index %%d %%d %%d -> %%d\n", B, i, j, idx); return 1; }
+                if (j > 32 * (i / 32) && idx != brr::gram_tile_index(B, i, j - 1) + 1) { printf("row not contiguous %%d %%d %%d\n", B, i, j); return 1; }
+                if (j == 32 * (i / 32) && i %% 32 == 0 && idx != brr::gram_subwindow_offset(B, i / 32)) { printf("offset %%d %%d\n", B, i); return 1; }
+            }
+        for (int v : seen) if (v != 1) { printf("hole %%d\n", B); return 1; }
+        printf("%%d %%d %%d\n", B, TE, brr::lookahead(B));
+    }
+    return 0;
+}
+''' % ROOT)
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    assert out[0].split()[:2] == ["32", "1024"] and out[1].split()[:2] == ["64", "3072"] and out[2].split()[:2] == ["128", "10240"]
+    for block in (32, 64, 128):
+        la = brr.lookahead(block)
+        assert la % 32 == 0 and 32 <= la <= block
+    with pytest.raises(ValueError):
+        brr.lookahead(48)
