@@ -84,7 +84,7 @@ def _synth_rows(N, M, seed, h2=0.5):
 
 
 def test_v2_config2_rows_column_sample(po, brr):
-    """BASELINE configs[1] rows: N = 50,000, default geometry (119 workers x 448 rows on a B200), M = 1,024 columns"""
+    """BASELINE configs[1] rows: N = 50,000, default geometry (98 workers x 512 rows on a B200), M = 1,024 columns"""
     N, M, T = 50000, 1024, 4
     X, y = _synth_rows(N, M, seed=430)
     o = po.run_v2(X, y, CVA, T, seed=431, **HYP)
