@@ -17,7 +17,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = (["-DBRR_ROUND_PROFILE=1"] if os.environ.get("BRR_ROUND_PROFILE") else []) + \
         (["-DBRR_TENSOR_DOTS=%s" % os.environ["BRR_TENSOR_DOTS"]] if os.environ.get("BRR_TENSOR_DOTS") else []) + \
         (["-DBRR_LOOKAHEAD128=%s" % os.environ["BRR_LOOKAHEAD128"]] if os.environ.get("BRR_LOOKAHEAD128") else []) + \
-        (["-DBRR_PHASE_PROFILE=1"] if os.environ.get("BRR_PHASE_PROFILE") else []) + (["-DBRR_DOT_PROFILE=1"] if os.environ.get("BRR_DOT_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        (["-DBRR_PHASE_PROFILE=1"] if os.environ.get("BRR_PHASE_PROFILE") else []) + \
+        (["-DBRR_COLUMN_STAGES=%s" % os.environ["BRR_COLUMN_STAGES"]] if os.environ.get("BRR_COLUMN_STAGES") else []) + \
+        (["-DBRR_MBAR_HANDOVER=%s" % os.environ["BRR_MBAR_HANDOVER"]] if os.environ.get("BRR_MBAR_HANDOVER") else []) + (["-DBRR_DOT_PROFILE=1"] if os.environ.get("BRR_DOT_PROFILE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "-Xptxas", "-v"]
 
 
