@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run every GPU test in its own process (a faulting kernel poisons the CUDA context of its process only).
-# usage: tools/gpu_each.sh [pytest -k expression]
+# usage: tools/gpu_jobs/each.sh [pytest -k expression]
 mkdir -p gpurun_out
 LOG=gpurun_out/gpu_each.log
 : > $LOG

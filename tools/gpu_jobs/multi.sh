@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU evidence: one-process-per-GPU parity test + torchrun bench at N GPUs; usage: tools/gpu_multi.sh N
+# multi-GPU evidence: one-process-per-GPU parity test + torchrun bench at N GPUs; usage: tools/gpu_jobs/multi.sh N
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_$N.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scaling evidence on one multi-GPU box: torchrun bench at each N given; usage: tools/gpu_scale.sh 8 4
+# scaling evidence on one multi-GPU box: torchrun bench at each N given; usage: tools/gpu_jobs/scale.sh 8 4
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_scale.log 2>&1
 for N in "$@"; do
