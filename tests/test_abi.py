@@ -261,3 +261,26 @@ int main()
         assert la % 32 == 0 and 32 <= la <= block
     with pytest.raises(ValueError):
         brr.lookahead(48)
+
+
+def test_bench_reference_arm_line_keeps_the_driver_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores; runs without a GPU): one JSON line with the arm's keys -- the
+    TIMED ms_per_step of the column sample, the extrapolated full-M figure under its own name, an e2e object that repeats the line's
+    value with zero copy bytes, and a cpu_baseline describing the run."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "SNP-updates/sec" and line["higher_is_better"] is True
+    assert line["steps"] == 1 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["dtype"] == "f64"
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["same_config"] is False
+    # the timed step is the sample's, the extrapolation scales it by M / sample_markers
+    assert abs(line["extrapolated_ms_per_iteration"] / line["ms_per_step"] - 50000 / line["sample_markers"]) < 1e-6
+    assert abs(line["value"] - line["sample_markers"] / (line["ms_per_step"] * 1e-3)) / line["value"] < 1e-6
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == line["value"] and "sample" in cb
+    assert "workload" in line["config"]
